@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""bench.py -- SGNS pair updates/sec of the ComEmb o2 hot path on B200 (BASELINE.json metric), with the roofline of
+the dominant kernel, an end-to-end number through host buffers, and the reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              our arm (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference [--gpus N] [--steps K] ...       the reference's own compiled Cython train_o2 on the
+                                                                      host cores (oracle/_ref; else the oracle port)
+
+Workload (BASELINE.json configs[1]): synthetic SBM, 100K nodes / ~2M edges / 50 blocks, d=128, walk length 80,
+window 10, 5 negatives.  One "step" = one pass of walks over every node of this rank's shard (walker kernel) + the
+Hogwild o2 kernel over those walks: 100 000 walks = 1.49e8 pair updates at N=1.  Tables are initialised like
+Model.reset_weights (model.py:86-87).  Weak scaling: every rank runs a full 100K-walk pass per step on its own walk
+stream and the replicated tables are averaged by an NCCL all-reduce every step.
+
+Timing: CUDA events on the launching stream around each step, an L2 flush (256 MiB write) between steps outside the
+events, >=3 warm-up steps, max over ranks.  Clocks / throttle reasons are sampled through NVML during the timed steps.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sgns_pair_updates_per_sec"
+UNIT = "pair-updates/s"
+B_PAIR = 4 * 128 * (2 + 2 * (5 + 1))  # algorithmic bytes per pair update at d=128, neg=5: 7168
+
+CFG = dict(n=100000, blocks=50, avg_degree=40, d=128, L=80, W=10, neg=5, lr=0.025, table_size=5000000,
+           graph_seed=12345)
+
+
+def pairs_of_len(length, W):
+    """Number of (centre, neighbour) pairs of one walk of `length` valid tokens (pyx:494-505)."""
+    i = np.arange(length)
+    return int((np.minimum(length, i + W + 1) - np.maximum(0, i - W) - 1).sum())
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons through NVML every 100 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # NVML missing: report it, do not fail the bench
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(node, ctx, table, walks, W, neg, lr, threads, seconds_budget=None):
+    """Time the reference's compiled train_o2 (oracle/_ref, `tuned` build) over `walks` (list of uint32 arrays) with
+    `threads` Python threads, the reference's own Hogwild scheme (context_embeddings.py:72-98).  Falls back to the
+    oracle port (C restatement, ctypes releases the GIL) when oracle/_ref is absent.  Returns (pairs/s, kind, info)."""
+    from oracle import oracle as O
+    kind = "reference" if O.ref_available("tuned") else "port"
+    d = node.shape[1]
+    total_pairs = sum(pairs_of_len(len(w), W) for w in walks)
+    shards = [walks[t::threads] for t in range(threads)]
+    if kind == "reference":
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        try:
+            from threadpoolctl import threadpool_limits
+            limiter = threadpool_limits(limits=1, user_api="blas")
+        except Exception:
+            limiter = None
+        ref = O.load_ref("tuned")
+        vocab = [O.RefVocab(i) for i in range(node.shape[0])]
+        paths = [[[vocab[t] for t in w.tolist()] for w in sh] for sh in shards]  # pre-built Vocab lists (untimed)
+
+        def work(t):
+            buf = np.zeros(d, np.float32)
+            for p in paths[t]:
+                ref.train_o2(node, ctx, p, lr, neg, W, table, py_alpha=1.0, py_size=d, py_work=buf)
+    else:
+        limiter = None
+        flats = []
+        for sh in shards:
+            off = np.zeros(len(sh) + 1, np.int64)
+            off[1:] = np.cumsum([len(w) for w in sh])
+            flats.append((np.ascontiguousarray(np.concatenate(sh), np.uint32), off,
+                          O.seeds_from_numpy(np.random.RandomState(1), len(sh))))
+
+        def work(t):
+            f, off, s = flats[t]
+            O.o2_walks(node, ctx, f, off, s, lr, neg, W, table, 1.0, O.DOT_REFBLAS_QUIRK)
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    del limiter
+    return total_pairs / dt, kind, dict(seconds=dt, pairs=total_pairs, walks=len(walks))
+
+
+def host_walks(G, n_walks, L, seed):
+    """Walks for the CPU arm, generated by the oracle's CPU walker when no GPU is needed (ROW tokens)."""
+    from oracle import oracle as O
+    passes = max(1, -(-n_walks // len(G)))
+    w, lens = O.walks(G.rowptr, G.col, passes, L, 0.0, seed)
+    return [w[i, :lens[i]].copy() for i in range(n_walks)]
+
+
+def build_workload():
+    from comemb_b200.utils import graph_utils as gu
+    G, block = gu.sbm_graph(CFG["n"], CFG["blocks"], CFG["avg_degree"], seed=CFG["graph_seed"])
+    return G, block
+
+
+def init_tables_host(n, d, seed=1):
+    rs = np.random.RandomState(seed)
+    node = rs.uniform(low=-1, high=1, size=(n, d)).astype(np.float32)  # model.py:86
+    ctx = np.zeros((n, d), np.float32)                                   # model.py:87
+    return node, ctx
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    from oracle import oracle as O
+    O.build()
+    G, _ = build_workload()
+    deg = np.diff(G.rowptr).astype(np.float64)
+    table = O.make_table(deg, CFG["table_size"])
+    node, ctx = init_tables_host(CFG["n"], CFG["d"])
+    threads = os.cpu_count() or 1
+    # bounded sample per step: ~4 s of CPU work per step at ~3e5 pairs/s/thread
+    walks_per_step = max(threads, min(CFG["n"], int(threads * 3e5 * 4 / pairs_of_len(CFG["L"], CFG["W"]))))
+    all_walks = host_walks(G, walks_per_step * (args.steps + args.warmup), CFG["L"], 7)
+    times, pairs, kind = [], 0, None
+    for s in range(args.warmup + args.steps):
+        ws = all_walks[s * walks_per_step:(s + 1) * walks_per_step]
+        v, kind, info = cpu_reference_run(node, ctx, table, ws, CFG["W"], CFG["neg"], CFG["lr"], threads)
+        if s >= args.warmup:
+            times.append(info["seconds"])
+            pairs += info["pairs"]
+    value = pairs / sum(times)
+    sample = "%d walks (%d pair updates) per step of the same SBM workload, %s" % (
+        walks_per_step, pairs // max(1, args.steps),
+        "reference Cython train_o2 (tuned build: legacy_implicit_noexcept, -O3)" if kind == "reference"
+        else "oracle C port")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[1]: synthetic SBM %dK nodes / ~2M edges / %d blocks, d=%d, walk len %d, "
+                        "window %d, %d negatives; one step = one walk per node (%d walks) per GPU" % (
+                            CFG["n"] // 1000, CFG["blocks"], CFG["d"], CFG["L"], CFG["W"], CFG["neg"], CFG["n"]),
+            "table_size": CFG["table_size"], "lr": CFG["lr"], "mode": "hogwild",
+            "l2": "256 MiB flush write between timed steps; tables 2x51 MB",
+            "parallelism": "replicated tables, walk stream sharded per GPU, NCCL all-reduce average every step"
+            if n_gpus > 1 else "single GPU"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the ComEmb B200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import comemb_b200.utils.training_sdg_inner as K
+    from comemb_b200.utils import graph_utils as gu
+    from comemb_b200 import _lib, replicas
+    K.init()
+    flags = K.F_ATOMIC if args.atomic else 0
+
+    G, _ = build_workload()
+    n, d, L, W, neg, lr = CFG["n"], CFG["d"], CFG["L"], CFG["W"], CFG["neg"], CFG["lr"]
+    deg = np.ascontiguousarray(np.diff(G.rowptr), np.float64)
+    table = torch.empty(CFG["table_size"], dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().comemb_make_table(deg.ctypes.data, deg.size, 0.75, table.data_ptr(), table.numel(), None))
+    node_h, ctx_h = init_tables_host(n, d)
+    node, ctx = torch.from_numpy(node_h).cuda(), torch.from_numpy(ctx_h).cuda()
+    rowptr, col = G.device()
+    walks = torch.empty((n, L), dtype=torch.int32, device="cuda")
+    lens = torch.empty(n, dtype=torch.int32, device="cuda")
+    off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    lib = _lib.load()
+    pairs_lut = torch.tensor([pairs_of_len(l, W) for l in range(L + 1)], dtype=torch.int64, device="cuda")
+
+    def step(s, ev=None):
+        """one pass: walker kernel (this rank's walk stream) + Hogwild o2 kernel [+ replica averaging]"""
+        g_first = (s * world + rank) * n  # distinct walk ids per (step, rank) -> distinct random streams
+        _lib.check(lib.comemb_walks_csr(rowptr.data_ptr(), col.data_ptr(), n, 1 << 20, L, 0.0, 777, K.MODE_HOGWILD,
+                                        g_first, n, walks.data_ptr(), lens.data_ptr(), stream.cuda_stream))
+        if ev:
+            ev[0].record(stream)
+        K.o2_batch(node, ctx, walks.reshape(-1), off, None, lr, neg, W, table, mode=K.MODE_HOGWILD, flags=flags,
+                   base_seed=1000003 * s + rank)
+        if ev:
+            ev[1].record(stream)
+        if world > 1:
+            replicas.average_tables([node, ctx], world=world)
+
+    for s in range(args.warmup):
+        step(s)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    step_ms, o2_ms, pairs = [], [], 0
+    for s in range(args.warmup, args.warmup + args.steps):
+        flush.fill_(s & 0xFF)  # L2 flush between timed steps, outside the events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        step(s, (k0, k1))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        pairs += int(pairs_lut[lens.long()].sum().item())  # exact pair count of this step's walks (untimed)
+        step_ms.append(e0.elapsed_time(e1))
+        o2_ms.append(k0.elapsed_time(k1))
+    clocks = sampler.result()
+    if world > 1:
+        dist.barrier()
+    t_total = torch.tensor([sum(step_ms), sum(o2_ms), float(pairs)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t_total.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t_total.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, o2_total_ms, all_pairs = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        total_ms, o2_total_ms, all_pairs = float(t_total[0]), float(t_total[1]), float(pairs)
+    value = all_pairs / (total_ms * 1e-3)
+
+    # ---- end-to-end through host buffers (pinned host memory -> device -> host, every step) ----------------------------
+    e2e = None
+    runner = K.HostO2Runner(n, d, n * L, n, table)
+    wh = walks.cpu().numpy().view(np.uint32).reshape(-1).copy()
+    offh = (np.arange(n + 1) * L).astype(np.int64)
+    nh, ch = node.cpu().numpy(), ctx.cpu().numpy()
+    e2e_pairs = int(pairs_lut[lens.long()].sum().item())
+    seeds_h = K.draw_seeds(n, np.random.RandomState(5))
+    ms = []
+    for s in range(1 + max(1, args.steps // 2)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h2d, d2h = runner.run(nh, ch, wh, offh, seeds_h, lr, neg, W, mode=K.MODE_HOGWILD, flags=flags)
+        if s:
+            ms.append(time.perf_counter() - t0)
+    e2e_t = torch.tensor([max(ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * e2e_pairs / float(e2e_t[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h),
+           "how": "HostO2Runner.run: numpy tables + walks -> pinned -> HBM, Hogwild o2 kernel, tables back to host"}
+    del runner
+
+    peak, peak_src = measured_peak()
+    o2_pairs_per_s = (all_pairs / world) / (o2_total_ms * 1e-3)  # per GPU, the dominant kernel alone
+    achieved = o2_pairs_per_s * B_PAIR / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "o2_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "o2_hogwild_kernel<1,true,%s>" % ("true" if args.atomic else "false"),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_pair": B_PAIR,
+                "pairs_per_launch": all_pairs / world / args.steps,
+                "kernel_ms_per_launch": o2_total_ms / args.steps,
+                "note": "tables (2 x 51 MB) fit the 126 MB L2: algorithmic bytes are served mostly by L2, so frac can "
+                        "exceed what DRAM alone would allow"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as O
+            threads = os.cpu_count() or 1
+            nw = max(threads, int(threads * 3e5 * 12 / pairs_of_len(L, W)))  # ~12 s of CPU work
+            nw = min(nw, n)
+            wnp = walks.cpu().numpy().view(np.uint32)
+            ln = lens.cpu().numpy()
+            ws = [wnp[i, :ln[i]].copy() for i in range(nw)]
+            tab_h = table.cpu().numpy().view(np.uint32)
+            v, kind, info = cpu_reference_run(node.cpu().numpy(), ctx.cpu().numpy(), tab_h, ws, W, neg, lr, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": "%d walks (%d pair updates) of the same workload, %.1f s, %s" % (
+                                        info["walks"], info["pairs"], info["seconds"],
+                                        "reference Cython train_o2, tuned build, one Python thread per core"
+                                        if kind == "reference" else "oracle C port, one thread per core")}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": "failed: %r" % (e,)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--atomic", type=int, default=0, help="1: scatter with red.global.add.v4.f32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

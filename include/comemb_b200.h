@@ -1,0 +1,141 @@
+/*
+ * comemb_b200.h -- C ABI of libcomemb_b200.so: the ComEmb SGD hot path (o1 / o2 / o3, walks, sampler tables) as
+ * hand-written sm_100a CUDA.  Plain pointers and sizes only; every pointer named d_* is a DEVICE pointer on the
+ * current CUDA device, `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * Each entry point names the reference interface it replaces ("pyx" = utils/training_sdg_inner.pyx of
+ * andompesta/nodeembedding-to-communityembedding).  The reference binds its hot path as a CPython extension module;
+ * the equivalent binding of this library is a ctypes stub, used by
+ * nodeembedding-to-communityembedding_b200/utils/training_sdg_inner.py.
+ *
+ * Return value: 0 = ok; <0 = COMEMB_E_* argument error; >0 = cudaError_t of the failed CUDA call.
+ * Calls are asynchronous on `stream` unless stated otherwise.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef COMEMB_B200_H
+#define COMEMB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COMEMB_ABI_VERSION 1
+
+#define COMEMB_TOKEN_NONE 0xFFFFFFFFu /* a `None` entry of a path (pyx:485-486) / padding of a short walk */
+
+/* error codes */
+#define COMEMB_E_ARG (-1)         /* null pointer / negative size / unsupported value */
+#define COMEMB_E_UNSUPPORTED (-2) /* e.g. Hogwild kernels need size <= 512 */
+#define COMEMB_E_NOINIT (-3)      /* comemb_init() not called on this device */
+
+/* execution modes */
+#define COMEMB_MODE_ORDERED 0 /* one logical stream: reproduces the reference's sequential updates exactly */
+#define COMEMB_MODE_HOGWILD 1 /* lock-free parallel SGD: one warp per walk / edge (the reference's worker threads) */
+
+/* flags (bit-or) */
+#define COMEMB_F_DOT_FLOAT 1u   /* ORDERED: model FAST_VERSION 1 (plain float sdot) instead of FAST_VERSION 0 (pyx:536-547) */
+#define COMEMB_F_ATOMIC 2u      /* HOGWILD: scatter with red.global.add.v4.f32 instead of plain stores */
+#define COMEMB_F_ALIAS 4u       /* HOGWILD: negatives from the alias table instead of the unigram table */
+#define COMEMB_F_SEED_HASH 8u   /* seeds==NULL: per-unit LCG seeds derived on device from base_seed */
+
+/* ---- module init: replaces `init()` + EXP_TABLE (pyx:92-95, 512-549) ------------------------------------------------
+ * Builds the 1000-entry sigmoid table on the host exactly as pyx:531-533 (double exp, float store) and uploads it
+ * to the current device.  Returns FAST_VERSION-compatible 0 on success (this library always models the float-table
+ * arithmetic; which sdot return convention ORDERED mode mimics is the COMEMB_F_DOT_FLOAT flag).  Synchronous. */
+int comemb_init(void);
+/* copy of the sigmoid table as uploaded (host buffer of 1000 floats); for tests */
+int comemb_get_lut(float *h_lut1000);
+int comemb_abi_version(void);
+/* Hogwild work decomposition: centres_per_unit = 0 -> one warp per walk (the reference's per-thread granularity);
+ * > 0 -> one warp per chunk of that many centres (needs max_walk_len); blocks_per_sm = 0 -> occupancy query. */
+int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm);
+const char *comemb_error_string(int code);
+
+/* ---- o2: replaces train_o2 (pyx:454-509) applied to a batch of paths, i.e. the worker loop of
+ * Context2Vec.train (ADSCModel/context_embeddings.py:83-84) -------------------------------------------------------------
+ * d_node, d_ctx : float32 [n_rows, size] row-major, updated in place (pyx:457-458)
+ * d_walks       : uint32 tokens = ROW indices (Vocab.index), COMEMB_TOKEN_NONE = None; walk w is
+ *                 d_walks[d_walk_off[w] .. d_walk_off[w+1])   (int64 offsets, n_walks+1 of them);
+ *                 only the first 10000 tokens of a walk are used (MAX_SENTENCE_LEN, pyx:18, 480)
+ * d_seeds       : uint64 per walk = (2^24)*randint(0,2^24)+randint(0,2^24) as pyx:477 draws it (host draws them in
+ *                 walk order); NULL with COMEMB_F_SEED_HASH -> derived from base_seed
+ * d_table       : uint32 [table_len] unigram^0.75 table whose VALUES are used as row indices (model.py:97-122)
+ * d_alias       : (COMEMB_F_ALIAS) uint32 [2*n_alias] = {threshold, alias} pairs from comemb_build_alias; else NULL
+ * lr, lambda    : py_lr, py_alpha of pyx:454 (g = (label - sigma)*lr*lambda, pyx:144)
+ * d_n_tokens    : optional int64[1]; receives sum of train_o2 return values (#non-None tokens, pyx:490)
+ * ORDERED: one warp replays all walks in order (bit-exact to the reference on its golden build).
+ * HOGWILD: one warp per walk (sequential inside the walk like a reference worker thread, walks concurrent). */
+int comemb_o2_walks(float *d_node, float *d_ctx, int64_t n_rows, int size, const uint32_t *d_walks,
+                    const int64_t *d_walk_off, int64_t n_walks, const uint64_t *d_seeds, uint64_t base_seed,
+                    const uint32_t *d_table, uint64_t table_len, const uint32_t *d_alias, uint32_t n_alias,
+                    int window, int negative, float lr, float lambda, int mode, uint32_t flags, int64_t *d_n_tokens,
+                    void *stream);
+
+/* ---- o1: replaces train_o1 (pyx:407-450) applied to a batch of edges, i.e. the worker loop of
+ * Node2Vec.train (ADSCModel/node_embeddings.py:70-71) -------------------------------------------------------------------
+ * d_edges : uint32 [n_edges, 2] row indices; per edge: update row e0 against target e1, then row e1 against the
+ *           updated e0, one LCG stream (pyx:444-448).  `edge_stride` (HOGWILD only, 0/1 = identity): edge number
+ *           u is taken as (u*edge_stride) mod n_edges so that concurrently running warps do not share a hub row. */
+int comemb_o1_edges(float *d_node, int64_t n_rows, int size, const uint32_t *d_edges, int64_t n_edges,
+                    const uint64_t *d_seeds, uint64_t base_seed, const uint32_t *d_table, uint64_t table_len,
+                    const uint32_t *d_alias, uint32_t n_alias, int negative, float lr, int mode, uint32_t flags,
+                    int64_t edge_stride, void *stream);
+
+/* ---- o3 (HEAD): replaces Community2Vec.train (ADSCModel/community_embeddings.py:61-77) ----------------------------------
+ * For every selected row r (d_rows, or all n_rows when NULL), `iters` times:
+ *    G = sum_k pi[r,k] * inv_cov[k] @ (x_r - mu_k);  x_r -= clip(G * (float)(beta/K), -5, 5) * lr
+ * d_inv_cov_t is inv_cov with each [size,size] block TRANSPOSED (comemb_transpose_blocks) so that lanes read it
+ * coalesced.  Exactly-zero pi entries are skipped (they contribute exactly 0). */
+int comemb_o3_batch(float *d_node, int64_t n_rows, int size, const uint32_t *d_rows, int64_t n_sel,
+                    const float *d_mu, const float *d_inv_cov_t, const float *d_pi, int K, double beta, float lr,
+                    int iters, void *stream);
+/* out[k][b][a] = in[k][a][b] for K blocks of size x size */
+int comemb_transpose_blocks(const float *d_in, float *d_out, int K, int size, void *stream);
+
+/* ---- legacy fused pass: replaces the stale train_sg (utils/training_sdg_inner.c:2736, 2988-3740; Python twin
+ * utils/embedding.py:15-72): per pair o3 gradient of x_j + SGNS pair + combined write ------------------------------------
+ * d_reduced_windows: int32 per token (np.random.randint(window) per token, drawn by the host) or NULL.
+ * inv_cov is read column-major as the reference's sgemm does, i.e. pass d_inv_cov UNtransposed. */
+int comemb_sg_fused(float *d_node, float *d_negemb, int64_t n_rows, int size, const uint32_t *d_walks,
+                    const int64_t *d_walk_off, int64_t n_walks, const int32_t *d_reduced_windows,
+                    const uint64_t *d_seeds, uint64_t base_seed, const uint32_t *d_table, uint64_t table_len,
+                    const float *d_mu, const float *d_inv_cov, const float *d_pi, int K, int window, int negative,
+                    float lr, float lambda1, float lambda2, int is_node_embedding, int mode, uint32_t flags,
+                    void *stream);
+
+/* ---- walks: replaces __random_walk__ / build_deepwalk_corpus_iter (utils/graph_utils.py:20-46, 191-197) -----------------
+ * CSR over row numbers: d_rowptr int64 [n+1], d_col uint32.  Output d_walks uint32 [num_paths*n, path_length] padded
+ * with COMEMB_TOKEN_NONE, d_lens int32 [num_paths*n].
+ * ORDERED: one thread replays CPython's random.Random(seed) (MT19937) stream: per pass a Fisher-Yates shuffle of the
+ *          start nodes, per step one random() and one choice() -- bit-exact walks.
+ * HOGWILD: one thread per walk, counter-based generator keyed by (seed, walk); start nodes are a per-pass
+ *          permutation; same walk distribution, different stream.
+ * first_walk/n_out select a contiguous shard of the num_paths*n walks (multi-GPU sharding; HOGWILD only). */
+int comemb_walks_csr(const int64_t *d_rowptr, const uint32_t *d_col, int64_t n, int num_paths, int path_length,
+                     double alpha, uint64_t seed, int mode, int64_t first_walk, int64_t n_out, uint32_t *d_walks,
+                     int32_t *d_lens, void *stream);
+
+/* ---- sampler tables: replaces Model.make_table (ADSCModel/model.py:97-122) ----------------------------------------------
+ * h_counts: HOST double [vocab_size] (node degree by row; the O(vocab) run-boundary recurrence runs on the host with
+ * the same libm pow() as CPython), d_table: DEVICE uint32 [table_size] filled by a kernel, with the reference's
+ * id-as-row quirk.  Bit-exact to the reference for contiguous ids 1..vocab_size.  Synchronous. */
+int comemb_make_table(const double *h_counts, int64_t vocab_size, double power, uint32_t *d_table, int64_t table_size,
+                      void *stream);
+/* alias table equivalent to drawing table[u % table_len] with u uniform: weights = run lengths of the table.
+ * d_alias uint32 [2*n_rows].  Synchronous (host-side Vose construction on the run lengths). */
+int comemb_build_alias(const uint32_t *d_table, int64_t table_len, int64_t n_rows, uint32_t *d_alias, void *stream);
+
+/* ---- multi-GPU replica averaging epilogue: x = x * scale (after an NCCL sum all-reduce) ---------------------------------- */
+int comemb_scale(float *d_x, int64_t n, float scale, void *stream);
+
+/* SGNS objective of a batch of walks (evaluation only; no reference counterpart for o2, mirrors Node2Vec.loss,
+ * node_embeddings.py:26-31, for window pairs): sum over pairs of -log sigmoid(x_j . c_i), exact sigmoid, double
+ * accumulation.  d_out: double[2] = {sum, n_pairs}. */
+int comemb_o2_pos_loss(const float *d_node, const float *d_ctx, int size, const uint32_t *d_walks,
+                       const int64_t *d_walk_off, int64_t n_walks, int window, double *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMEMB_B200_H */

@@ -1,0 +1,58 @@
+"""Community2Vec: GMM fit + community-gradient step (/root/reference/ADSCModel/community_embeddings.py:12-77).
+
+`train(nodes, model, beta, chunksize, iter)` runs csrc/o3_community.cu.  `fit` stays sklearn's GaussianMixture on the
+host exactly as the reference (:16-37) -- it is the producer of o3's inputs, not part of the SGD path.
+"""
+import logging as log
+
+import numpy as np
+
+from ..utils import training_sdg_inner as K
+
+
+class Community2Vec(object):
+    def __init__(self, model, lr, reg_covar=0):
+        self.lr = lr
+        self.reg_covar = reg_covar
+        self.k = model.k
+        self.g_mixture = None
+
+    def fit(self, model):
+        import sklearn.mixture as mixture
+        import torch
+        log.info("Fitting: {} communities".format(model.k))
+        if self.g_mixture is None:
+            self.g_mixture = mixture.GaussianMixture(n_components=model.k, reg_covar=self.reg_covar,
+                                                     covariance_type='full', n_init=10)
+        x = model.node_embedding.detach().cpu().numpy()
+        self.g_mixture.fit(x)
+        dev = model.node_embedding.device
+        model.centroid = torch.from_numpy(self.g_mixture.means_.astype(np.float32)).to(dev)
+        cov = self.g_mixture.covariances_.astype(np.float32)
+        model.covariance_mat = torch.from_numpy(cov).to(dev)
+        model.inv_covariance_mat = torch.from_numpy(np.linalg.inv(cov).astype(np.float32)).to(dev)
+        model.pi = torch.from_numpy(self.g_mixture.predict_proba(x).astype(np.float32)).to(dev)
+
+    def loss(self, nodes, model, beta, chunksize=150):
+        """sum_i sum_k pi_ik * log N(x_i | mu_k, Sigma_k), scaled by beta/K (the intent of
+        community_embeddings.py:40-59, whose own code raises: `model.vocab(x)`)."""
+        import torch
+        rows = torch.as_tensor([model.vocab[x].index for x in nodes], dtype=torch.int64,
+                               device=model.node_embedding.device)
+        x = model.node_embedding[rows].double()
+        total = 0.0
+        for com in range(model.k):
+            mvn = torch.distributions.MultivariateNormal(model.centroid[com].double(),
+                                                         covariance_matrix=model.covariance_mat[com].double())
+            total += float((mvn.log_prob(x) * model.pi[rows, com].double()).sum().item())
+        return abs(total) * (beta / model.k)
+
+    def train(self, nodes, model, beta, chunksize=150, iter=1):
+        import torch
+        dev = model.node_embedding.device
+        rows = np.fromiter((model.vocab[x].index for x in nodes), dtype=np.uint32)
+        rows_d = torch.from_numpy(rows.view(np.int32)).to(dev)
+        with torch.cuda.device(dev):
+            inv_t = K.transpose_blocks(model.inv_covariance_mat.contiguous())
+            K.o3_batch(model.node_embedding, rows_d, model.centroid.contiguous(), inv_t, model.pi.contiguous(), beta,
+                       self.lr, iters=iter)

@@ -1,0 +1,93 @@
+"""ctypes binding of csrc/libcomemb_b200.so (the C ABI declared in include/comemb_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises, and every entry point raises
+`ComembError` on a non-zero status.  Device memory, streams and multi-GPU plumbing come from PyTorch.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libcomemb_b200.so")
+
+TOKEN_NONE = 0xFFFFFFFF
+MODE_ORDERED, MODE_HOGWILD = 0, 1
+F_DOT_FLOAT, F_ATOMIC, F_ALIAS, F_SEED_HASH = 1, 2, 4, 8
+
+# every symbol include/comemb_b200.h declares: (restype, argtypes)
+_c = ctypes
+_vp, _i32, _i64, _u32, _u64, _f32, _f64 = (_c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint32, _c.c_uint64, _c.c_float,
+                                           _c.c_double)
+SIGNATURES = {
+    "comemb_init": (_i32, []),
+    "comemb_get_lut": (_i32, [_vp]),
+    "comemb_abi_version": (_i32, []),
+    "comemb_set_tuning": (_i32, [_i32, _i32, _i32]),
+    "comemb_error_string": (_c.c_char_p, [_i32]),
+    "comemb_o2_walks": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _u64, _vp, _u64, _vp, _u32, _i32, _i32,
+                               _f32, _f32, _i32, _u32, _vp, _vp]),
+    "comemb_o1_edges": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _u64, _vp, _u64, _vp, _u32, _i32, _f32, _i32, _u32,
+                               _i64, _vp]),
+    "comemb_o3_batch": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _f64, _f32, _i32, _vp]),
+    "comemb_transpose_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "comemb_sg_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32,
+                               _i32, _i32, _f32, _f32, _f32, _i32, _i32, _u32, _vp]),
+    "comemb_walks_csr": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _u64, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "comemb_make_table": (_i32, [_vp, _i64, _f64, _vp, _i64, _vp]),
+    "comemb_build_alias": (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    "comemb_scale": (_i32, [_vp, _i64, _f32, _vp]),
+    "comemb_o2_pos_loss": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp]),
+}
+
+
+class ComembError(RuntimeError):
+    pass
+
+
+_lib = None
+_inited_devices = set()
+
+
+def load():
+    """Load the shared library (no CUDA call is made)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ComembError(
+                "%s is missing: build it with `python -m %s.build` (nvcc, sm_100a). There is no CPU fallback."
+                % (LIB_PATH, "comemb_b200"))
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().comemb_error_string(status)
+        raise ComembError("libcomemb_b200: status %d: %s" % (status, msg.decode() if msg else "?"))
+
+
+def ensure_init():
+    """comemb_init() once per device (the `FAST_VERSION = init()` of pyx:549)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise ComembError("no CUDA device: the ComEmb B200 path has no CPU fallback")
+    dev = torch.cuda.current_device()
+    if dev not in _inited_devices:
+        torch.cuda.init()
+        torch.zeros(1, device="cuda")  # make sure the primary context is current
+        check(load().comemb_init())
+        _inited_devices.add(dev)
+    return 0
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

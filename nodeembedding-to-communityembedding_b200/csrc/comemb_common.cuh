@@ -1,0 +1,88 @@
+// comemb_common.cuh -- shared device helpers of the ComEmb B200 hot path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/comemb_b200.h"
+
+#define EXP_TABLE_SIZE 1000  // pyx:89
+#define MAX_EXP_F 6.0f       // pyx:90
+#define MAX_SENTENCE_LEN 10000  // pyx:18
+#define LCG_MUL 25214903917ULL  // pyx:134
+#define LCG_MASK 281474976710655ULL  // pyx:121
+#define FULL 0xffffffffu
+
+// The sigmoid table of pyx:92-95 / 531-533 lives in a per-device global buffer uploaded by comemb_init(); kernels
+// receive its pointer and stage it into shared memory.  nullptr until comemb_init() ran on the current device.
+const float *comemb_lut_device();
+
+#define CUDA_TRY(x)                        \
+    do {                                   \
+        cudaError_t _e = (x);              \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+// ---- LCG of pyx:133-134 ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t lcg_next(uint64_t x) { return (x * LCG_MUL + 11ULL) & LCG_MASK; }
+
+// x advanced n steps in O(log n): composition of affine maps mod 2^48.
+__device__ __forceinline__ uint64_t lcg_skip(uint64_t x, uint64_t n) {
+    uint64_t a = LCG_MUL, c = 11ULL, A = 1ULL, C = 0ULL;
+    while (n) {
+        if (n & 1ULL) {
+            A = A * a;
+            C = C * a + c;
+        }
+        c = (a + 1ULL) * c;
+        a = a * a;
+        n >>= 1;
+    }
+    return (A * x + C) & LCG_MASK;
+}
+
+// (next_random >> 16) % table_len  (pyx:133).  The state has 48 bits, so the dividend is a 32-bit value.
+struct TableMod {
+    uint64_t len;    // table_len
+    uint64_t magic;  // ceil(2^64 / len) for len < 2^32 (Lemire fastmod), 0 otherwise
+};
+static inline TableMod make_table_mod(uint64_t len) {
+    TableMod m;
+    m.len = len;
+    m.magic = (len > 1 && len <= 0xFFFFFFFFULL) ? (0xFFFFFFFFFFFFFFFFULL / len + 1ULL) : 0ULL;
+    return m;
+}
+__device__ __forceinline__ uint64_t table_slot(uint64_t next_random, const TableMod &m) {
+    uint64_t a = next_random >> 16;  // < 2^32
+    if (m.magic) return __umul64hi(m.magic * a, m.len);
+    return m.len == 1 ? 0ULL : a;  // len >= 2^32 > a
+}
+
+// sigma lookup of pyx:143: EXP_TABLE[(int)((f + 6.0) * 83)] with the double arithmetic of the generated C.
+__device__ __forceinline__ int lut_index(float f) { return __double2int_rz(((double)f + 6.0) * 83.0); }
+
+__device__ __forceinline__ float warp_sum_xor(float v) {
+    v += __shfl_xor_sync(FULL, v, 16);
+    v += __shfl_xor_sync(FULL, v, 8);
+    v += __shfl_xor_sync(FULL, v, 4);
+    v += __shfl_xor_sync(FULL, v, 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    return v;
+}
+
+// splitmix64: per-unit seed derivation for COMEMB_F_SEED_HASH and the Hogwild walker.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+// red.global.add.v4.f32 (sm_90+): one 16-byte vector reduction, no return value.
+__device__ __forceinline__ void red_add4(float *p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+int comemb_check_init();  // COMEMB_E_NOINIT unless comemb_init() ran on the current device

@@ -1,0 +1,464 @@
+// sgns_hogwild.cu -- HOGWILD mode of o1 / o2 on sm_100a: lock-free SGD, one warp per reference "worker job".
+//
+// Mapping (Context2Vec.train's worker threads, context_embeddings.py:72-98 -> warps):
+//   * one warp owns one walk (or one centre-chunk of a walk) and replays it sequentially exactly like train_o2
+//     (pyx:494-508): same pair order, same LCG stream (chunks start at the right stream position via O(log n) LCG
+//     skip-ahead, so the negative-sample indices are those the reference would draw from the same seed);
+//   * walks run concurrently and race on shared rows without locks, as the reference's threads do.
+// Data movement per pair (the roofline's 7168 B at size=128, neg=5): the node row and neg+1 context rows are
+// gathered with one 128-bit load per lane per row (a 512 B row = one fully coalesced warp request), all negative
+// rows of a pair are in flight together, dots are reduced with xor-shuffles, sigma comes from the 1000-entry table
+// staged in shared memory, rows are scattered back with 128-bit stores (or red.global.add.v4.f32 with
+// COMEMB_F_ATOMIC).  The positive context row of a centre stays in registers across its whole window.
+// Table rows are loaded with ld.global.cg (L2-coherent): other warps' updates are seen as soon as they reach L2.
+#include "comemb_common.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int NEGB = 5;  // negatives gathered per batch (neg=5 -> one batch)
+
+struct Tuning {
+    int centres_per_unit = 0;  // 0 = a whole walk per warp
+    int max_walk_len = 0;      // needed when centres_per_unit > 0
+    int blocks_per_sm = 0;     // 0 = occupancy query
+};
+Tuning g_tuning;
+
+template <int NCH>
+struct Row {
+    float v[4 * NCH];
+};
+
+template <int NCH, bool VEC>
+__device__ __forceinline__ Row<NCH> row_load(const float *p, int d, int lane) {
+    Row<NCH> r;
+#pragma unroll
+    for (int m = 0; m < NCH; m++) {
+        const int base = 128 * m + 4 * lane;
+        if (VEC) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (base < d) q = ldcg4(p + base);
+            r.v[4 * m + 0] = q.x; r.v[4 * m + 1] = q.y; r.v[4 * m + 2] = q.z; r.v[4 * m + 3] = q.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) r.v[4 * m + c] = (base + c < d) ? __ldcg(p + base + c) : 0.f;
+        }
+    }
+    return r;
+}
+
+template <int NCH, bool VEC>
+__device__ __forceinline__ void row_store(float *p, const Row<NCH> &r, int d, int lane) {
+#pragma unroll
+    for (int m = 0; m < NCH; m++) {
+        const int base = 128 * m + 4 * lane;
+        if (VEC) {
+            if (base < d) st4(p + base, make_float4(r.v[4 * m], r.v[4 * m + 1], r.v[4 * m + 2], r.v[4 * m + 3]));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (base + c < d) p[base + c] = r.v[4 * m + c];
+        }
+    }
+}
+
+template <int NCH, bool VEC>
+__device__ __forceinline__ void row_red(float *p, const Row<NCH> &r, int d, int lane) {
+#pragma unroll
+    for (int m = 0; m < NCH; m++) {
+        const int base = 128 * m + 4 * lane;
+        if (VEC) {
+            if (base < d) red_add4(p + base, make_float4(r.v[4 * m], r.v[4 * m + 1], r.v[4 * m + 2], r.v[4 * m + 3]));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (base + c < d) atomicAdd(p + base + c, r.v[4 * m + c]);
+        }
+    }
+}
+
+// lane-local part of the canonical dot: fma chain over the lane's elements in increasing order, from +0
+template <int NCH>
+__device__ __forceinline__ float dot_part(const Row<NCH> &a, const Row<NCH> &b) {
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4 * NCH; e++) acc = fmaf(a.v[e], b.v[e], acc);
+    return acc;
+}
+
+template <int NCH>
+__device__ __forceinline__ void row_fma(Row<NCH> &y, float a, const Row<NCH> &x) {  // y += a*x
+#pragma unroll
+    for (int e = 0; e < 4 * NCH; e++) y.v[e] = fmaf(a, x.v[e], y.v[e]);
+}
+
+template <int NCH>
+__device__ __forceinline__ Row<NCH> row_scaled(float a, const Row<NCH> &x) {
+    Row<NCH> r;
+#pragma unroll
+    for (int e = 0; e < 4 * NCH; e++) r.v[e] = __fmul_rn(a, x.v[e]);
+    return r;
+}
+
+template <int NCH>
+__device__ __forceinline__ Row<NCH> row_zero() {
+    Row<NCH> r;
+#pragma unroll
+    for (int e = 0; e < 4 * NCH; e++) r.v[e] = 0.f;
+    return r;
+}
+
+struct Draw {
+    const uint32_t *table;
+    TableMod mod;
+    const uint32_t *alias;  // {threshold, alias} pairs or nullptr
+    uint32_t n_alias;
+};
+
+// One negative drawn from LCG state r (pyx:133): the table slot, or with the alias sampler the (bucket, coin) pair
+// taken from the same 32 random bits.
+__device__ __forceinline__ uint32_t draw_fetch(const Draw &D, uint64_t r) {
+    if (D.alias) {
+        const uint64_t a = (r >> 16) * (uint64_t)D.n_alias;  // 32-bit uniform x n -> bucket in the high word
+        const uint32_t bucket = (uint32_t)(a >> 32), coin = (uint32_t)a;
+        const uint2 e = __ldg(reinterpret_cast<const uint2 *>(D.alias) + bucket);
+        return coin < e.x ? bucket : e.y;
+    }
+    return __ldg(D.table + table_slot(r, D.mod));
+}
+
+__device__ __forceinline__ float sgns_g(float f, float label, float lr, float lambda, const float *lut) {
+    return __fmul_rn(__fmul_rn(label - lut[lut_index(f)], lr), lambda);  // pyx:143-144
+}
+
+// ---- o2 -------------------------------------------------------------------------------------------------------------------
+struct O2Params {
+    float *node, *ctx;
+    int d;
+    const uint32_t *walks;
+    const int64_t *walk_off;
+    int64_t n_walks;
+    const uint64_t *seeds;
+    uint64_t base_seed;
+    Draw draw;
+    int window, negative;
+    float lr, lambda;
+    int centres_per_unit, units_per_walk;
+    int64_t *n_tokens;
+    const float *glut;
+};
+
+template <int NCH, bool VEC, bool ATOMIC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) o2_hogwild_kernel(const O2Params P) {
+    __shared__ float lut[EXP_TABLE_SIZE];
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int d = P.d, W = P.window, negative = P.negative;
+    const int64_t n_units = P.n_walks * P.units_per_walk;
+    const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+
+    for (int64_t u = warp0; u < n_units; u += n_warps) {
+        const int64_t w = u / P.units_per_walk;
+        const int q = (int)(u - w * P.units_per_walk);
+        const uint32_t *path = P.walks + P.walk_off[w];
+        int len = (int)min((int64_t)MAX_SENTENCE_LEN, P.walk_off[w + 1] - P.walk_off[w]);  // pyx:480
+        const int c0 = P.centres_per_unit ? q * P.centres_per_unit : 0;
+        const int c1 = P.centres_per_unit ? min(len, c0 + P.centres_per_unit) : len;
+        if (c0 >= len) continue;
+        uint64_t rnd = P.seeds ? P.seeds[w] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        if (q == 0 && P.n_tokens) {  // train_o2's return value (pyx:490)
+            int cnt = 0;
+            for (int i = lane; i < len; i += 32) cnt += (__ldg(path + i) != COMEMB_TOKEN_NONE);
+            cnt = __reduce_add_sync(FULL, cnt);
+            if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(P.n_tokens), (unsigned long long)cnt);
+        }
+        if (c0 > 0) {  // position of this chunk in the walk's LCG stream: `negative` draws per preceding pair
+            int pairs = 0;
+            for (int i = lane; i < c0; i += 32) {
+                if (__ldg(path + i) == COMEMB_TOKEN_NONE) continue;
+                const int j1 = min(len, i + W + 1);
+                for (int j = max(0, i - W); j < j1; j++) pairs += (j != i && __ldg(path + j) != COMEMB_TOKEN_NONE);
+            }
+            pairs = __reduce_add_sync(FULL, pairs);
+            rnd = lcg_skip(rnd, (uint64_t)pairs * (uint64_t)negative);
+        }
+
+        for (int i = c0; i < c1; i++) {  // pyx:494
+            const uint32_t wi = __ldg(path + i);
+            if (wi == COMEMB_TOKEN_NONE) continue;
+            float *pos_ptr = P.ctx + (int64_t)wi * d;
+            Row<NCH> cpos = row_load<NCH, VEC>(pos_ptr, d, lane);
+            Row<NCH> dpos = row_zero<NCH>();  // ATOMIC: accumulated delta of the positive row
+            const int j1 = min(len, i + W + 1);
+            for (int j = max(0, i - W); j < j1; j++) {  // pyx:503
+                const uint32_t wj = __ldg(path + j);
+                if (j == i || wj == COMEMB_TOKEN_NONE) continue;
+                float *row1_ptr = P.node + (int64_t)wj * d;
+                const Row<NCH> row1 = row_load<NCH, VEC>(row1_ptr, d, lane);
+                Row<NCH> work = row_zero<NCH>();
+                // positive target (label 1), pyx:129-131
+                {
+                    const float f = warp_sum_xor(dot_part<NCH>(row1, cpos));
+                    if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+                        const float g = sgns_g(f, 1.f, P.lr, P.lambda, lut);
+                        row_fma<NCH>(work, g, cpos);  // pyx:146
+                        if (ATOMIC) row_fma<NCH>(dpos, g, row1);
+                        row_fma<NCH>(cpos, g, row1);  // pyx:147 (kept in registers)
+                    }
+                }
+                for (int kb = 0; kb < negative; kb += NEGB) {
+                    const int nb = min(NEGB, negative - kb);
+                    // draw nb negatives: every lane steps the LCG, lane k fetches sample k (pyx:133-134)
+                    uint64_t mine = 0;
+#pragma unroll
+                    for (int k = 0; k < NEGB; k++)
+                        if (k < nb) {
+                            if (lane == k) mine = rnd;
+                            rnd = lcg_next(rnd);
+                        }
+                    uint32_t tmine = (lane < nb) ? draw_fetch(P.draw, mine) : 0u;
+                    uint32_t t[NEGB];
+                    bool act[NEGB];
+                    Row<NCH> c[NEGB];
+#pragma unroll
+                    for (int k = 0; k < NEGB; k++) {
+                        t[k] = __shfl_sync(FULL, tmine, k);
+                        act[k] = (k < nb) && (t[k] != wi);  // pyx:135-136
+                        if (act[k]) c[k] = row_load<NCH, VEC>(P.ctx + (int64_t)t[k] * d, d, lane);
+                    }
+                    float f[NEGB];
+#pragma unroll
+                    for (int k = 0; k < NEGB; k++) f[k] = act[k] ? dot_part<NCH>(row1, c[k]) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < NEGB; k++) f[k] = warp_sum_xor(f[k]);
+#pragma unroll
+                    for (int k = 0; k < NEGB; k++) {
+                        if (!act[k]) continue;
+                        bool dup = false;  // an earlier sample of this batch hit the same row: it must see that update
+#pragma unroll
+                        for (int a = 0; a < k; a++)
+                            if (act[a] && t[a] == t[k]) {
+                                c[k] = c[a];
+                                dup = true;
+                            }
+                        float fk = f[k];
+                        if (dup) fk = warp_sum_xor(dot_part<NCH>(row1, c[k]));
+                        if (fk <= -MAX_EXP_F || fk >= MAX_EXP_F) continue;  // pyx:141-142
+                        const float g = sgns_g(fk, 0.f, P.lr, P.lambda, lut);
+                        row_fma<NCH>(work, g, c[k]);  // pyx:146
+                        float *cp = P.ctx + (int64_t)t[k] * d;
+                        if (ATOMIC) row_red<NCH, VEC>(cp, row_scaled<NCH>(g, row1), d, lane);
+                        row_fma<NCH>(c[k], g, row1);  // pyx:147
+                        if (!ATOMIC) row_store<NCH, VEC>(cp, c[k], d, lane);
+                    }
+                }
+                // pyx:149
+                if (ATOMIC) {
+                    row_red<NCH, VEC>(row1_ptr, work, d, lane);
+                } else {
+                    Row<NCH> r = row1;
+#pragma unroll
+                    for (int e = 0; e < 4 * NCH; e++) r.v[e] = r.v[e] + work.v[e];
+                    row_store<NCH, VEC>(row1_ptr, r, d, lane);
+                }
+            }
+            if (ATOMIC)
+                row_red<NCH, VEC>(pos_ptr, dpos, d, lane);
+            else
+                row_store<NCH, VEC>(pos_ptr, cpos, d, lane);
+        }
+    }
+}
+
+// ---- o1 -------------------------------------------------------------------------------------------------------------------
+struct O1Params {
+    float *node;
+    int d;
+    const uint32_t *edges;
+    int64_t n_edges;
+    const uint64_t *seeds;
+    uint64_t base_seed;
+    Draw draw;
+    int negative;
+    float lr;
+    int64_t stride;
+    const float *glut;
+};
+
+// One directed update (fast_o1, pyx:205-249) with row1 already in registers.  `other_idx/other` = a row this warp
+// holds a newer copy of than global memory might (the row it updated a moment ago); samples equal to it use that copy.
+template <int NCH, bool VEC>
+__device__ __forceinline__ Row<NCH> o1_directed(const O1Params &P, const float *lut, int lane, uint32_t word_index,
+                                                const Row<NCH> &target_row, const Row<NCH> &row1, uint32_t other_idx,
+                                                const Row<NCH> &other, bool has_other, uint64_t &rnd) {
+    const int d = P.d;
+    Row<NCH> work = row_zero<NCH>();
+    {
+        const float f = warp_sum_xor(dot_part<NCH>(row1, target_row));
+        if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+            const float g = __fmul_rn(1.f - lut[lut_index(f)], P.lr);  // pyx:243
+            row_fma<NCH>(work, g, target_row);                         // pyx:245
+        }
+    }
+    for (int kb = 0; kb < P.negative; kb += NEGB) {
+        const int nb = min(NEGB, P.negative - kb);
+        uint64_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < NEGB; k++)
+            if (k < nb) {
+                if (lane == k) mine = rnd;
+                rnd = lcg_next(rnd);
+            }
+        const uint32_t tmine = (lane < nb) ? draw_fetch(P.draw, mine) : 0u;
+        Row<NCH> c[NEGB];
+        bool act[NEGB];
+#pragma unroll
+        for (int k = 0; k < NEGB; k++) {
+            const uint32_t t = __shfl_sync(FULL, tmine, k);
+            act[k] = (k < nb) && (t != word_index);
+            if (act[k]) {
+                if (has_other && t == other_idx)
+                    c[k] = other;
+                else
+                    c[k] = row_load<NCH, VEC>(P.node + (int64_t)t * d, d, lane);
+            }
+        }
+        float f[NEGB];
+#pragma unroll
+        for (int k = 0; k < NEGB; k++) f[k] = act[k] ? dot_part<NCH>(row1, c[k]) : 0.f;
+#pragma unroll
+        for (int k = 0; k < NEGB; k++) f[k] = warp_sum_xor(f[k]);
+#pragma unroll
+        for (int k = 0; k < NEGB; k++) {
+            if (!act[k] || f[k] <= -MAX_EXP_F || f[k] >= MAX_EXP_F) continue;
+            const float g = __fmul_rn(0.f - lut[lut_index(f[k])], P.lr);
+            row_fma<NCH>(work, g, c[k]);
+        }
+    }
+    return work;
+}
+
+template <int NCH, bool VEC, bool ATOMIC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) o1_hogwild_kernel(const O1Params P) {
+    __shared__ float lut[EXP_TABLE_SIZE];
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int d = P.d;
+    const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+    for (int64_t u = warp0; u < P.n_edges; u += n_warps) {
+        const int64_t q = P.stride > 1 ? (int64_t)(((uint64_t)u * (uint64_t)P.stride) % (uint64_t)P.n_edges) : u;  // both < 2^32
+        const uint32_t e0 = __ldg(P.edges + 2 * q), e1 = __ldg(P.edges + 2 * q + 1);
+        uint64_t rnd = P.seeds ? P.seeds[q] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)q)) & LCG_MASK);
+        float *p0 = P.node + (int64_t)e0 * d, *p1 = P.node + (int64_t)e1 * d;
+        Row<NCH> r0 = row_load<NCH, VEC>(p0, d, lane);
+        Row<NCH> r1 = (e1 == e0) ? r0 : row_load<NCH, VEC>(p1, d, lane);
+        // pyx:444: row e0 against target e1
+        Row<NCH> work = o1_directed<NCH, VEC>(P, lut, lane, e1, r1, r0, 0u, r0, false, rnd);
+        if (ATOMIC) row_red<NCH, VEC>(p0, work, d, lane);
+#pragma unroll
+        for (int e = 0; e < 4 * NCH; e++) r0.v[e] = r0.v[e] + work.v[e];
+        if (!ATOMIC) row_store<NCH, VEC>(p0, r0, d, lane);
+        if (e1 == e0) r1 = r0;
+        // pyx:447: row e1 against the UPDATED row e0 (held in registers)
+        work = o1_directed<NCH, VEC>(P, lut, lane, e0, r0, r1, e0, r0, true, rnd);
+        if (ATOMIC) {
+            row_red<NCH, VEC>(p1, work, d, lane);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4 * NCH; e++) r1.v[e] = r1.v[e] + work.v[e];
+            row_store<NCH, VEC>(p1, r1, d, lane);
+        }
+    }
+}
+
+template <typename K>
+int grid_for(K kernel, int64_t n_units) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, 0);
+    if (g_tuning.blocks_per_sm > 0) per_sm = g_tuning.blocks_per_sm;
+    if (per_sm < 1) per_sm = 1;
+    int64_t want = (n_units + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    int64_t cap = (int64_t)sms * per_sm;  // a multiple of the SM count: every SM holds its full complement of warps
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <int NCH, bool VEC>
+int launch_o2_t(const O2Params &P, bool atomic, cudaStream_t st) {
+    const int64_t n_units = P.n_walks * P.units_per_walk;
+    if (atomic) {
+        auto k = o2_hogwild_kernel<NCH, VEC, true>;
+        k<<<grid_for(k, n_units), WARPS_PER_BLOCK * 32, 0, st>>>(P);
+    } else {
+        auto k = o2_hogwild_kernel<NCH, VEC, false>;
+        k<<<grid_for(k, n_units), WARPS_PER_BLOCK * 32, 0, st>>>(P);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <int NCH, bool VEC>
+int launch_o1_t(const O1Params &P, bool atomic, cudaStream_t st) {
+    if (atomic) {
+        auto k = o1_hogwild_kernel<NCH, VEC, true>;
+        k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);
+    } else {
+        auto k = o1_hogwild_kernel<NCH, VEC, false>;
+        k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+void hogwild_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm) {
+    g_tuning.centres_per_unit = centres_per_unit;
+    g_tuning.max_walk_len = max_walk_len;
+    g_tuning.blocks_per_sm = blocks_per_sm;
+}
+
+int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, const int64_t *walk_off,
+                      int64_t n_walks, const uint64_t *seeds, uint64_t base_seed, const uint32_t *table,
+                      uint64_t table_len, const uint32_t *alias, uint32_t n_alias, int window, int negative, float lr,
+                      float lambda, bool atomic, int64_t *n_tokens, cudaStream_t st) {
+    if (size > 512) return COMEMB_E_UNSUPPORTED;
+    if (n_walks == 0) return 0;
+    O2Params P;
+    P.node = node; P.ctx = ctx; P.d = size; P.walks = walks; P.walk_off = walk_off; P.n_walks = n_walks;
+    P.seeds = seeds; P.base_seed = base_seed;
+    P.draw = Draw{table, make_table_mod(table_len), alias, n_alias};
+    P.window = window; P.negative = negative; P.lr = lr; P.lambda = lambda;
+    P.centres_per_unit = 0; P.units_per_walk = 1;
+    if (g_tuning.centres_per_unit > 0 && g_tuning.max_walk_len > 0) {
+        P.centres_per_unit = g_tuning.centres_per_unit;
+        P.units_per_walk = (g_tuning.max_walk_len + P.centres_per_unit - 1) / P.centres_per_unit;
+    }
+    P.n_tokens = n_tokens;
+    P.glut = comemb_lut_device();
+    const bool vec = (size % 4) == 0;
+    if (size <= 128) return vec ? launch_o2_t<1, true>(P, atomic, st) : launch_o2_t<1, false>(P, atomic, st);
+    if (size <= 256) return vec ? launch_o2_t<2, true>(P, atomic, st) : launch_o2_t<2, false>(P, atomic, st);
+    return vec ? launch_o2_t<4, true>(P, atomic, st) : launch_o2_t<4, false>(P, atomic, st);
+}
+
+int launch_o1_hogwild(float *node, int size, const uint32_t *edges, int64_t n_edges, const uint64_t *seeds,
+                      uint64_t base_seed, const uint32_t *table, uint64_t table_len, const uint32_t *alias,
+                      uint32_t n_alias, int negative, float lr, bool atomic, int64_t stride, cudaStream_t st) {
+    if (size > 512) return COMEMB_E_UNSUPPORTED;
+    if (n_edges == 0) return 0;
+    O1Params P;
+    P.node = node; P.d = size; P.edges = edges; P.n_edges = n_edges; P.seeds = seeds; P.base_seed = base_seed;
+    P.draw = Draw{table, make_table_mod(table_len), alias, n_alias};
+    if (stride > 1 && n_edges > 0xFFFFFFFFLL) return COMEMB_E_UNSUPPORTED;
+    P.negative = negative; P.lr = lr; P.stride = stride > 1 ? stride % n_edges : 0;
+    P.glut = comemb_lut_device();
+    const bool vec = (size % 4) == 0;
+    if (size <= 128) return vec ? launch_o1_t<1, true>(P, atomic, st) : launch_o1_t<1, false>(P, atomic, st);
+    if (size <= 256) return vec ? launch_o1_t<2, true>(P, atomic, st) : launch_o1_t<2, false>(P, atomic, st);
+    return vec ? launch_o1_t<4, true>(P, atomic, st) : launch_o1_t<4, false>(P, atomic, st);
+}

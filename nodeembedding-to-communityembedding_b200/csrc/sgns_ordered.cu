@@ -1,0 +1,323 @@
+// sgns_ordered.cu -- ORDERED mode of o1 / o2 (and the legacy fused pass): one warp replays the reference's
+// sequential update stream, bit-for-bit.
+//
+// What "bit-for-bit" means here: the reference computes dot products through BLAS sdot and updates through BLAS
+// saxpy (pyx:140, 146-149).  The golden vectors were produced with OpenBLAS' SkylakeX kernels; dot_refblas() below
+// performs the same fp32 operations in the same association order (four 16-lane FMA accumulators per 64 elements,
+// 16->8 fold, an optional 32-element block on 8-lane accumulators, ((a0+a1)+a2)+a3, 8->4 fold, two horizontal adds,
+// <32-element tail in double) and, for FAST_VERSION 0 (pyx:536-541), the "float return register read as a double"
+// reinterpretation.  saxpy is one FMA per element.  Every step is an IEEE-754 operation with a single defined
+// rounding, so the device result equals the CPU result exactly.
+//
+// This is a correctness mode: a single warp, no parallelism across pairs (pair p+1 must see every write of pair p).
+#include "comemb_common.cuh"
+
+namespace {
+
+// ---- dot product in the reference's summation order ---------------------------------------------------------------------
+// x, y: rows in global memory, previously written (possibly by other lanes of this warp) and made visible by
+// __syncwarp().  Returns the value on every lane.
+__device__ float dot_refblas(const float *x, const float *y, int n, bool quirk) {
+    const int lane = threadIdx.x & 31;
+    // accumulator q = 16k+l of the four 16-lane vectors lives on lane q%32, register q/32
+    float a0 = 0.f, a1 = 0.f;
+    const int n64 = n & ~63;
+    int i = 0;
+    for (; i < n64; i += 64) {
+        a0 = fmaf(x[i + lane], y[i + lane], a0);
+        a1 = fmaf(x[i + 32 + lane], y[i + 32 + lane], a1);
+    }
+    // fold 16 -> 8 lanes: acc_k[l] = a5_k[l] + a5_k[l+8]; valid on lanes with (lane%16) < 8
+    a0 = a0 + __shfl_down_sync(FULL, a0, 8);
+    a1 = a1 + __shfl_down_sync(FULL, a1, 8);
+    // now: a0 on lanes 0..7 = acc_0, lanes 16..23 = acc_1; a1 on lanes 0..7 = acc_2, lanes 16..23 = acc_3
+    const int n32 = n & ~31;
+    if (i < n32) {  // at most one block of 32: acc_k[l] = fma(x[i+8k+l], y[i+8k+l], acc_k[l])
+        const int l = lane & 7;
+        const bool hi = (lane & 16) != 0;  // lanes 16..23 hold k=1 (a0) and k=3 (a1)
+        if ((lane & 8) == 0) {
+            const int e0 = i + (hi ? 8 : 0) + l;
+            const int e1 = i + (hi ? 24 : 16) + l;
+            a0 = fmaf(x[e0], y[e0], a0);
+            a1 = fmaf(x[e1], y[e1], a1);
+        }
+        i += 32;
+    }
+    // v[l] = ((acc0[l] + acc1[l]) + acc2[l]) + acc3[l] on lanes 0..7
+    float v = a0 + __shfl_down_sync(FULL, a0, 16);
+    v = v + a1;
+    v = v + __shfl_down_sync(FULL, a1, 16);
+    // h[l] = v[l] + v[l+4], l < 4 ; my = (h0 + h1) + (h2 + h3)
+    float h = v + __shfl_down_sync(FULL, v, 4);
+    float p = h + __shfl_down_sync(FULL, h, 1);
+    float my = p + __shfl_down_sync(FULL, p, 2);
+    my = __shfl_sync(FULL, my, 0);
+    // tail in double from fp32 products, then + (double)my
+    double dot = 0.0;
+    for (; i < n; i++) dot = __dadd_rn(dot, (double)__fmul_rn(y[i], x[i]));
+    dot = __dadd_rn(dot, (double)my);
+    float fl = __double2float_rn(dot);
+    if (!quirk) return fl;
+    // FAST_VERSION 0: caller reads xmm0 as a double = {upper half of the double intermediate, float bit pattern}
+    double seen = __hiloint2double(__double2hiint(dot), __float_as_int(fl));
+    return __double2float_rn(seen);
+}
+
+// y += a*x over n elements, one FMA each, lane-strided.
+__device__ __forceinline__ void axpy_rows(int n, float a, const float *x, float *y) {
+    for (int e = threadIdx.x & 31; e < n; e += 32) y[e] = fmaf(a, x[e], y[e]);
+}
+
+struct Sampler {
+    const uint32_t *table;
+    TableMod mod;
+};
+
+// fast_o2 (pyx:105-151).  work: shared memory [size].
+__device__ uint64_t pair_o2(const Sampler &S, float *node, float *ctx, int size, uint32_t word_index,
+                            uint32_t word2_index, float lr, float lambda, float *work, uint64_t next_random,
+                            int negative, bool quirk, const float *lut) {
+    const int lane = threadIdx.x & 31;
+    float *row1 = node + (int64_t)word2_index * size;
+    for (int e = lane; e < size; e += 32) work[e] = 0.f;  // pyx:126
+    __syncwarp();
+    for (int d = 0; d < negative + 1; d++) {
+        uint32_t target;
+        float label;
+        if (d == 0) {
+            target = word_index;
+            label = 1.f;
+        } else {
+            target = S.table[table_slot(next_random, S.mod)];  // pyx:133
+            next_random = lcg_next(next_random);                // pyx:134
+            if (target == word_index) continue;                 // pyx:135-136
+            label = 0.f;
+        }
+        float *row2 = ctx + (int64_t)target * size;
+        float f = dot_refblas(row1, row2, size, quirk);  // pyx:140
+        if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;  // pyx:141-142
+        f = lut[lut_index(f)];                            // pyx:143
+        float g = __fmul_rn(__fmul_rn(label - f, lr), lambda);  // pyx:144
+        axpy_rows(size, g, row2, work);  // pyx:146
+        axpy_rows(size, g, row1, row2);  // pyx:147
+        __syncwarp();
+    }
+    for (int e = lane; e < size; e += 32) row1[e] = row1[e] + work[e];  // pyx:149 (saxpy with alpha=1)
+    __syncwarp();
+    return next_random;
+}
+
+// fast_o1 (pyx:205-249): targets are rows of the node table and are not updated.
+__device__ uint64_t pair_o1(const Sampler &S, float *node, int size, uint32_t word_index, uint32_t word2_index,
+                            float lr, float *work, uint64_t next_random, int negative, bool quirk,
+                            const float *lut) {
+    const int lane = threadIdx.x & 31;
+    float *row1 = node + (int64_t)word2_index * size;
+    for (int e = lane; e < size; e += 32) work[e] = 0.f;
+    __syncwarp();
+    for (int d = 0; d < negative + 1; d++) {
+        uint32_t target;
+        float label;
+        if (d == 0) {
+            target = word_index;
+            label = 1.f;
+        } else {
+            target = S.table[table_slot(next_random, S.mod)];
+            next_random = lcg_next(next_random);
+            if (target == word_index) continue;
+            label = 0.f;
+        }
+        const float *row2 = node + (int64_t)target * size;
+        float f = dot_refblas(row1, row2, size, quirk);
+        if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
+        f = lut[lut_index(f)];
+        float g = __fmul_rn(label - f, lr);  // pyx:243
+        axpy_rows(size, g, row2, work);      // pyx:245
+        __syncwarp();
+    }
+    for (int e = lane; e < size; e += 32) row1[e] = row1[e] + work[e];  // pyx:247
+    __syncwarp();
+    return next_random;
+}
+
+__global__ void __launch_bounds__(32) o2_ordered_kernel(float *node, float *ctx, int size, const uint32_t *walks,
+                                                        const int64_t *walk_off, int64_t n_walks,
+                                                        const uint64_t *seeds, uint64_t base_seed, Sampler S,
+                                                        int window, int negative, float lr, float lambda, bool quirk,
+                                                        int64_t *n_tokens, const float *g_exp_table) {
+    extern __shared__ float smem[];
+    float *lut = smem;                    // [1000]
+    float *work = smem + EXP_TABLE_SIZE;  // [size]
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
+    __syncwarp();
+    int64_t tokens = 0;
+    for (int64_t w = 0; w < n_walks; w++) {  // context_embeddings.py:83-84: paths in order, one worker
+        const uint32_t *path = walks + walk_off[w];
+        int64_t len = walk_off[w + 1] - walk_off[w];
+        if (len > MAX_SENTENCE_LEN) len = MAX_SENTENCE_LEN;  // pyx:480
+        uint64_t next_random = seeds ? seeds[w] : (splitmix64(base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        for (int64_t i = 0; i < len; i++) {  // pyx:494
+            const uint32_t wi = path[i];
+            if (wi == COMEMB_TOKEN_NONE) continue;
+            tokens++;
+            int64_t j = i - window;
+            if (j < 0) j = 0;
+            int64_t k = i + window + 1;
+            if (k > len) k = len;
+            for (; j < k; j++) {  // pyx:503
+                const uint32_t wj = path[j];
+                if (j == i || wj == COMEMB_TOKEN_NONE) continue;
+                next_random = pair_o2(S, node, ctx, size, wi, wj, lr, lambda, work, next_random, negative, quirk, lut);
+            }
+        }
+    }
+    if (n_tokens && threadIdx.x == 0) *n_tokens += tokens;
+}
+
+__global__ void __launch_bounds__(32) o1_ordered_kernel(float *node, int size, const uint32_t *edges, int64_t n_edges,
+                                                        const uint64_t *seeds, uint64_t base_seed, Sampler S,
+                                                        int negative, float lr, bool quirk, const float *g_exp_table) {
+    extern __shared__ float smem[];
+    float *lut = smem;
+    float *work = smem + EXP_TABLE_SIZE;
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
+    __syncwarp();
+    for (int64_t q = 0; q < n_edges; q++) {  // node_embeddings.py:70-71
+        const uint32_t e0 = edges[2 * q], e1 = edges[2 * q + 1];
+        uint64_t next_random = seeds ? seeds[q] : (splitmix64(base_seed ^ splitmix64((uint64_t)q)) & LCG_MASK);
+        next_random = pair_o1(S, node, size, e1, e0, lr, work, next_random, negative, quirk, lut);  // pyx:444
+        next_random = pair_o1(S, node, size, e0, e1, lr, work, next_random, negative, quirk, lut);  // pyx:447
+    }
+}
+
+// ---- legacy fused pass (stale train_sg; training_sdg_inner.c:1597-1905, 2520-2715, 2988-3740) ----------------------------
+// smem: lut[1000] | work[size] | work_o3[size]
+__global__ void __launch_bounds__(32)
+    sg_fused_ordered_kernel(float *node, float *negemb, int size, const uint32_t *walks, const int64_t *walk_off,
+                            int64_t n_walks, const int32_t *reduced_windows, const uint64_t *seeds,
+                            uint64_t base_seed, Sampler S, const float *mu, const float *inv_cov, const float *pi, int K,
+                            int window, int negative, float lr, float lambda1, float lambda2, int is_node_embedding,
+                            bool quirk, const float *g_exp_table) {
+    extern __shared__ float smem[];
+    float *lut = smem;
+    float *work = lut + EXP_TABLE_SIZE;
+    float *work_o3 = work + size;
+    const int lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
+    __syncwarp();
+    const float clipv = __fmul_rn(0.1f, lr);  // c:2556
+    const float nl2 = -lambda2;               // c:3132
+    for (int64_t w = 0; w < n_walks; w++) {
+        const uint32_t *path = walks + walk_off[w];
+        const int32_t *rw = reduced_windows ? reduced_windows + walk_off[w] : nullptr;
+        int64_t len = walk_off[w + 1] - walk_off[w];
+        if (len > MAX_SENTENCE_LEN) len = MAX_SENTENCE_LEN;
+        uint64_t next_random = seeds ? seeds[w] : (splitmix64(base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        for (int64_t i = 0; i < len; i++) {
+            const uint32_t wi = path[i];
+            if (wi == COMEMB_TOKEN_NONE) continue;
+            const int r = rw ? rw[i] : 0;
+            int64_t j = i - window + r;
+            if (j < 0) j = 0;
+            int64_t k = i + window + 1 - r;
+            if (k > len) k = len;
+            for (; j < k; j++) {
+                const uint32_t wj = path[j];
+                if (j == i || wj == COMEMB_TOKEN_NONE) continue;
+                float *row1 = node + (int64_t)wj * size;
+                // (1) o3 gradient of x_j from its current value; lanes own outputs a = lane, lane+32, ...
+                for (int e = lane; e < size; e += 32) work_o3[e] = 0.f;
+                if (nl2 != 0.f) {
+                    for (int a = lane; a < size; a += 32) {
+                        double acc = 0.0;
+                        for (int c = 0; c < K; c++) {
+                            const float p = pi[(int64_t)wj * K + c];
+                            const float *Sm = inv_cov + (int64_t)c * size * size;
+                            const float *m = mu + (int64_t)c * size;
+                            double t = 0.0;
+                            for (int b = 0; b < size; b++) {
+                                const float df = row1[b] - m[b];
+                                t = __dadd_rn(t, __dmul_rn((double)__fmul_rn(p, Sm[(int64_t)b * size + a]), (double)df));
+                            }
+                            acc = __dadd_rn(acc, t);
+                        }
+                        float v = __fmul_rn(nl2, __double2float_rn(acc));
+                        work_o3[a] = v < -clipv ? -clipv : (v > clipv ? clipv : v);
+                    }
+                }
+                // (2) SGNS pair
+                for (int e = lane; e < size; e += 32) work[e] = 0.f;
+                __syncwarp();
+                for (int d = 0; d < negative + 1; d++) {
+                    uint32_t target;
+                    float label;
+                    if (d == 0) {
+                        target = wi;
+                        label = 1.f;
+                    } else {
+                        target = S.table[table_slot(next_random, S.mod)];
+                        next_random = lcg_next(next_random);
+                        if (target == wi) continue;
+                        label = 0.f;
+                    }
+                    float *row2 = negemb + (int64_t)target * size;
+                    float f = dot_refblas(row1, row2, size, quirk);
+                    if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
+                    f = lut[lut_index(f)];
+                    const float g = __fmul_rn(label - f, lr);  // c:1813
+                    const float gl = __fmul_rn(g, lambda1);    // c:1822
+                    axpy_rows(size, g, row2, work);
+                    if (!is_node_embedding) axpy_rows(size, gl, row1, row2);  // c:1840-1859
+                    __syncwarp();
+                }
+                for (int e = lane; e < size; e += 32) {
+                    float v = fmaf(lambda1, work[e], row1[e]);  // c:1870
+                    row1[e] = v + work_o3[e];                    // c:3668
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ---- launchers (called from capi.cu) -------------------------------------------------------------------------------------
+int launch_o2_ordered(float *node, float *ctx, int size, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
+                      const uint64_t *seeds, uint64_t base_seed, const uint32_t *table, uint64_t table_len, int window,
+                      int negative, float lr, float lambda, bool quirk, int64_t *n_tokens, cudaStream_t st) {
+    Sampler S{table, make_table_mod(table_len)};
+    size_t smem = (EXP_TABLE_SIZE + (size_t)size) * sizeof(float);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(o2_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    o2_ordered_kernel<<<1, 32, smem, st>>>(node, ctx, size, walks, walk_off, n_walks, seeds, base_seed, S, window,
+                                           negative, lr, lambda, quirk, n_tokens, comemb_lut_device());
+    return (int)cudaGetLastError();
+}
+
+int launch_o1_ordered(float *node, int size, const uint32_t *edges, int64_t n_edges, const uint64_t *seeds,
+                      uint64_t base_seed, const uint32_t *table, uint64_t table_len, int negative, float lr, bool quirk,
+                      cudaStream_t st) {
+    Sampler S{table, make_table_mod(table_len)};
+    size_t smem = (EXP_TABLE_SIZE + (size_t)size) * sizeof(float);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(o1_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    o1_ordered_kernel<<<1, 32, smem, st>>>(node, size, edges, n_edges, seeds, base_seed, S, negative, lr, quirk,
+                                           comemb_lut_device());
+    return (int)cudaGetLastError();
+}
+
+int launch_sg_fused_ordered(float *node, float *negemb, int size, const uint32_t *walks, const int64_t *walk_off,
+                            int64_t n_walks, const int32_t *reduced_windows, const uint64_t *seeds, uint64_t base_seed,
+                            const uint32_t *table, uint64_t table_len, const float *mu, const float *inv_cov,
+                            const float *pi, int K, int window, int negative, float lr, float lambda1, float lambda2,
+                            int is_node_embedding, bool quirk, cudaStream_t st) {
+    Sampler S{table, make_table_mod(table_len)};
+    size_t smem = (EXP_TABLE_SIZE + 2 * (size_t)size) * sizeof(float);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(sg_fused_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sg_fused_ordered_kernel<<<1, 32, smem, st>>>(node, negemb, size, walks, walk_off, n_walks, reduced_windows, seeds,
+                                                 base_seed, S, mu, inv_cov, pi, K, window, negative, lr, lambda1,
+                                                 lambda2, is_node_embedding, quirk, comemb_lut_device());
+    return (int)cudaGetLastError();
+}

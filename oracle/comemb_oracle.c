@@ -245,32 +245,33 @@ int64_t oracle_o1_edges(float *node, int size, const uint32_t *edges, int64_t n_
  * grad_i = sum_k pi[i,k] * inv_cov[k] @ (x_i - mu_k)  from x frozen at the start of each iter;
  * x -= clip(grad * beta/K, -5, 5) * lr.  `rows` = model.vocab[node].index for the nodes passed in (duplicates add up,
  * as `grad_input[node_index] += ...` does per chunk -- within one chunk numpy's fancy += keeps only the last duplicate;
- * the callers pass each node once, and so do we).  Accumulation in double then rounded: the reference's own order
- * (numpy matmul on [n,d,d]x[n,d,1]) is BLAS-dependent, tests compare at 1e-5 relative. */
+ * the callers pass each node once, and so do we).  Each [d]x[d,d] product is summed in double then rounded to float32,
+ * communities accumulate in float32 like batch_grad_input: the reference's own order inside np.matmul
+ * ([n,d,d]x[n,d,1]) is BLAS-dependent, tests compare at 1e-5 relative. */
 void oracle_o3_batch(float *node, int64_t n_rows, int size, const uint32_t *rows, int64_t n_sel, const float *mu,
-                     const float *inv_cov, const float *pi, int K, float beta, float lr, int iters) {
+                     const float *inv_cov, const float *pi, int K, double beta, float lr, int iters) {
     float *grad = (float *)malloc((size_t)n_rows * size * sizeof(float));
-    double *acc = (double *)malloc((size_t)size * sizeof(double));
+    float *acc = (float *)malloc((size_t)size * sizeof(float));
     float *diff = (float *)malloc((size_t)size * sizeof(float));
     for (int it = 0; it < iters; it++) {
         memset(grad, 0, (size_t)n_rows * size * sizeof(float));
         for (int64_t s = 0; s < n_sel; s++) {
             int64_t r = rows[s];
             const float *x = node + r * size;
-            for (int a = 0; a < size; a++) acc[a] = 0.0;
+            for (int a = 0; a < size; a++) acc[a] = 0.0f; /* :66 batch_grad_input (float32) */
             for (int k = 0; k < K; k++) {
                 float p = pi[r * K + k];
                 for (int b = 0; b < size; b++) diff[b] = x[b] - mu[(int64_t)k * size + b]; /* :68 */
                 const float *S = inv_cov + (int64_t)k * size * size;
-                for (int a = 0; a < size; a++) { /* :69-71  m = pi*inv_cov ; m @ diff */
+                for (int a = 0; a < size; a++) { /* :69-71  m = pi*inv_cov (float32) ; m @ diff */
                     double t = 0.0;
                     for (int b = 0; b < size; b++) t += (double)(float)(p * S[(int64_t)a * size + b]) * (double)diff[b];
-                    acc[a] += (double)(float)t;
+                    acc[a] += (float)t; /* :72 float32 += */
                 }
             }
-            for (int a = 0; a < size; a++) grad[r * size + a] += (float)acc[a]; /* :72 */
+            for (int a = 0; a < size; a++) grad[r * size + a] += acc[a]; /* :73 */
         }
-        float scale = beta / (float)K; /* :76 (python float beta/k, then float32 array * python float -> float32) */
+        float scale = (float)(beta / (double)K); /* :76 float32 array *= python float (beta/k) */
         for (int64_t e = 0; e < n_rows * size; e++) {
             float g = grad[e] * scale;
             g = g < -5.0f ? -5.0f : (g > 5.0f ? 5.0f : g); /* :77 */

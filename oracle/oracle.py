@@ -49,7 +49,7 @@ def lib():
         L.oracle_o2_walks.restype = i64
         L.oracle_o1_edges.argtypes = [vp, i32, vp, i64, vp, f32, i32, vp, u64, i32]
         L.oracle_o1_edges.restype = i64
-        L.oracle_o3_batch.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, i32, f32, f32, i32]
+        L.oracle_o3_batch.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, i32, f64, f32, i32]
         L.oracle_make_table.argtypes = [vp, i64, i64, f64, vp, i64]
         L.oracle_walk_file_seed.argtypes = [u64]
         L.oracle_walk_file_seed.restype = u64

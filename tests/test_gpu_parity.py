@@ -1,0 +1,429 @@
+"""GPU parity tests (run with -m gpu on a B200).  Every test calls the CUDA path through the C ABI
+(libcomemb_b200.so via comemb_b200._lib) and checks it against
+
+  * the committed golden vectors produced by the reference itself (tests/golden/*.npz), and
+  * the CPU oracle (oracle/comemb_oracle.c) on the same seeded inputs.
+
+Bars: ORDERED o1/o2, walks, table: BIT-EXACT (np.array_equal on fp32 tables / uint32 indices).
+      o3: 1e-5 relative (fp32 matmul order of the reference's BLAS is unspecified); bit-exact vs the oracle.
+      HOGWILD: bit-exact vs the oracle's warp-order model when a single warp runs (no races); statistical otherwise.
+"""
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import comemb_b200.utils.training_sdg_inner as k
+    k.init()
+    return k
+
+
+def dev(a):
+    import torch
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    if a.dtype == np.uint64:
+        a = a.view(np.int64)
+    return torch.from_numpy(a).cuda()
+
+
+def host(t, dtype=None):
+    a = t.detach().cpu().numpy()
+    return a.view(dtype) if dtype is not None else a
+
+
+def test_lut_matches_oracle(K):
+    import ctypes
+    from comemb_b200 import _lib
+    out = np.empty(1000, np.float32)
+    _lib.check(_lib.load().comemb_get_lut(out.ctypes.data_as(ctypes.c_void_p)))
+    assert np.array_equal(out, O.init_lut())
+    assert K.FAST_VERSION == 0 and K.REAL is np.float32
+
+
+@pytest.mark.parametrize("name", sorted(cases.O2_CASES))
+def test_o2_ordered_bit_exact_vs_reference_golden(K, golden, name):
+    c = cases.O2_CASES[name]
+    node, ctx, table, walks = cases.o2_inputs(c)
+    flat, off = cases.flatten_walks(walks)
+    seeds = O.seeds_from_numpy(np.random.RandomState(c["seed"] + 7), len(walks))
+    dn, dc = dev(node), dev(ctx)
+    tok = K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), c["lr"], c["neg"], c["W"], dev(table), alpha=c["lam"],
+                     mode=K.MODE_ORDERED, count_tokens=True)
+    g = golden["sgd"]
+    assert tok == int(g[name + "/ret"])
+    assert np.array_equal(host(dn), g[name + "/node"])
+    assert np.array_equal(host(dc), g[name + "/ctx"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.O1_CASES))
+def test_o1_ordered_bit_exact_vs_reference_golden(K, golden, name):
+    c = cases.O1_CASES[name]
+    node, table, edges = cases.o1_inputs(c)
+    seeds = O.seeds_from_numpy(np.random.RandomState(c["seed"] + 7), len(edges))
+    dn = dev(node)
+    K.o1_batch(dn, dev(edges), dev(seeds), c["lr"], c["neg"], dev(table), mode=K.MODE_ORDERED)
+    assert np.array_equal(host(dn), golden["sgd"][name + "/node"])
+
+
+def test_o2_ordered_float_sdot_flavour_matches_oracle(K):
+    """FAST_VERSION-1 flavour (plain float sdot): no golden machine here, pinned against the oracle's model."""
+    c = cases.O2_CASES["o2_d128_small"]
+    node, ctx, table, walks = cases.o2_inputs(c)
+    flat, off = cases.flatten_walks(walks)
+    seeds = O.seeds_from_numpy(np.random.RandomState(1), len(walks))
+    dn, dc = dev(node), dev(ctx)
+    K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), c["lr"], c["neg"], c["W"], dev(table), mode=K.MODE_ORDERED,
+               flags=K.F_DOT_FLOAT)
+    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], c["neg"], c["W"], table, 1.0, O.DOT_REFBLAS)
+    assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+
+
+@pytest.mark.parametrize("name", sorted(cases.O2_CASES))
+def test_per_call_train_o2_numpy_in_place(K, golden, name):
+    """The reference's own calling convention: numpy tables borrowed and updated in place, one call per path, seeds
+    from the global np.random stream (pyx:477)."""
+    c = cases.O2_CASES[name]
+    if c["nw"] * c["L"] > 2500:
+        pytest.skip("per-call path exercised on the small cases")
+    node, ctx, table, walks = cases.o2_inputs(c)
+    np.random.seed(c["seed"] + 7)
+    tot = 0
+    for w in walks:
+        path = [None if int(t) == cases.TOKEN_NONE else O.RefVocab(int(t)) for t in w]
+        tot += K.train_o2(node, ctx, path, c["lr"], c["neg"], c["W"], table, py_alpha=c["lam"], py_size=c["d"],
+                          py_work=np.zeros(c["d"], np.float32))
+    g = golden["sgd"]
+    assert tot == int(g[name + "/ret"])
+    assert np.array_equal(node, g[name + "/node"]) and np.array_equal(ctx, g[name + "/ctx"])
+
+
+def test_per_call_train_o1_numpy_in_place(K, golden):
+    name = "o1_d100_selfloops"
+    c = cases.O1_CASES[name]
+    node, table, edges = cases.o1_inputs(c)
+    np.random.seed(c["seed"] + 7)
+    tot = 0
+    for e in edges:
+        tot += K.train_o1(node, [O.RefVocab(int(e[0])), O.RefVocab(int(e[1]))], c["lr"], c["neg"], table,
+                          py_size=c["d"], py_work=np.zeros(c["d"], np.float32))
+    assert tot == int(golden["sgd"][name + "/ret"])
+    assert np.array_equal(node, golden["sgd"][name + "/node"])
+
+
+def test_error_behaviour(K):
+    import torch
+    node = np.zeros((4, 8), np.float64)
+    with pytest.raises(K.ComembError):
+        K.train_o2(node, node, [O.RefVocab(0)], 0.1, 1, 1, np.ones(4, np.uint32), py_size=8)
+    n32 = np.zeros((4, 8), np.float32)
+    with pytest.raises(K.ComembError):
+        K.train_o2(n32, n32.copy(), [O.RefVocab(0)], 0.1, 1, 1, np.ones(4, np.uint32), py_size=16)
+    with pytest.raises(K.ComembError):  # Hogwild kernels: size <= 512
+        big = torch.zeros((4, 1024), device="cuda")
+        K.o2_batch(big, big.clone(), dev(np.zeros(2, np.uint32)), dev(np.array([0, 2], np.int64)), None, 0.1, 1, 1,
+                   dev(np.ones(4, np.uint32)), mode=K.MODE_HOGWILD)
+    # ORDERED handles any size
+    big = torch.rand((4, 1024), device="cuda") * 0.01
+    K.o2_batch(big, big.clone(), dev(np.array([0, 1], np.uint32)), dev(np.array([0, 2], np.int64)),
+               dev(np.array([5], np.uint64)), 0.1, 1, 1, dev(np.ones(4, np.uint32)), mode=K.MODE_ORDERED)
+
+
+@pytest.mark.parametrize("name", sorted(cases.O3_CASES))
+def test_o3_batch(K, golden, name):
+    c = cases.O3_CASES[name]
+    node, mu, inv, pi, rows = cases.o3_inputs(c)
+    dn = dev(node)
+    K.o3_batch(dn, dev(rows), dev(mu), K.transpose_blocks(dev(inv)), dev(pi), c["beta"], c["lr"], iters=c["iters"])
+    got = host(dn)
+    want = golden["sgd"][name + "/node"]
+    assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max())  # vs the reference (numpy) itself
+    O.o3_batch(node, rows, mu, inv, pi, c["beta"], c["lr"], c["iters"])
+    assert np.array_equal(got, node)  # vs the oracle: same arithmetic, bit for bit
+
+
+@pytest.mark.parametrize("name", ["walks_a0", "walks_a02", "walks_len1", "walks_bigseed"])
+def test_walks_ordered_bit_exact(K, golden, name):
+    import comemb_b200.utils.graph_utils as gu
+    g = golden["walks"]
+    num_paths, L, seed = (int(v) for v in g[name + "/params"])
+    G = gu.from_csr(g["karate/ids"], g["karate/rowptr"], g["karate/col"])
+    walks, lens = gu.build_deepwalk_corpus(G, num_paths, L, alpha=float(g[name + "/alpha"]), seed=seed,
+                                           mode=gu.MODE_ORDERED)
+    assert np.array_equal(walks, g[name + "/walks"])
+    assert np.array_equal(lens, (g[name + "/walks"] != cases.TOKEN_NONE).sum(1))
+
+
+def test_walks_hogwild_properties(K, golden):
+    import comemb_b200.utils.graph_utils as gu
+    g = golden["walks"]
+    G = gu.from_csr(g["karate/ids"], g["karate/rowptr"], g["karate/col"])
+    n, P, L = len(G), 6, 30
+    walks, lens = gu.build_deepwalk_corpus(G, P, L, alpha=0.0, seed=99, mode=gu.MODE_HOGWILD)
+    assert walks.shape == (P * n, L) and (lens == L).all()
+    for p in range(P):  # every node starts exactly one walk per pass
+        assert sorted(walks[p * n:(p + 1) * n, 0].tolist()) == list(range(n))
+    adj = [set(g["karate/col"][g["karate/rowptr"][i]:g["karate/rowptr"][i + 1]].tolist()) for i in range(n)]
+    for w in walks:
+        for a, b in zip(w[:-1], w[1:]):
+            assert int(b) in adj[int(a)]
+    # next-node choice is uniform over neighbours: chi-square-ish check on the highest-degree node
+    hub = int(np.argmax(np.diff(g["karate/rowptr"])))
+    walks, _ = gu.build_deepwalk_corpus(G, 400, 10, alpha=0.0, seed=5, mode=gu.MODE_HOGWILD)
+    nxt = walks[:, 1:][walks[:, :-1] == hub]
+    counts = np.bincount(nxt, minlength=n)[sorted(adj[hub])]
+    exp = counts.sum() / len(adj[hub])
+    assert counts.sum() > 2000 and np.abs(counts - exp).max() < 6 * np.sqrt(exp)
+    # restarts: alpha=1 -> always back to the start node
+    walks, _ = gu.build_deepwalk_corpus(G, 2, 8, alpha=1.0, seed=5, mode=gu.MODE_HOGWILD)
+    assert (walks == walks[:, :1]).all()
+    # shards of the walk space reproduce the full run
+    full, _ = gu.build_deepwalk_corpus(G, 4, 12, alpha=0.1, seed=7, mode=gu.MODE_HOGWILD)
+    part, _ = gu.build_deepwalk_corpus(G, 4, 12, alpha=0.1, seed=7, mode=gu.MODE_HOGWILD, first_walk=50, n_out=40)
+    assert np.array_equal(full[50:90], part)
+
+
+@pytest.mark.parametrize("name", ["table_small", "table_powerlaw"])
+def test_make_table_bit_exact(K, golden, name):
+    import torch
+    from comemb_b200 import _lib
+    g = golden["sgd"]
+    counts = np.ascontiguousarray(g[name + "/counts"], np.float64)
+    size = int(g[name + "/size"])
+    t = torch.empty(size, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().comemb_make_table(counts.ctypes.data, counts.size, 0.75, t.data_ptr(), size, None))
+    table = host(t, np.uint32)
+    starts = np.flatnonzero(np.concatenate([[True], table[1:] != table[:-1]]))
+    assert np.array_equal(table[starts], g[name + "/vals"]) and np.array_equal(starts, g[name + "/starts"])
+    assert np.array_equal(table, O.make_table(counts, size))
+
+
+def test_karate_config1_through_learners(K, golden):
+    """BASELINE.json configs[0]: the reference's karate run (d=128) through OUR Model / Node2Vec / Context2Vec /
+    Community2Vec, compared stage by stage with what the reference's learners produced."""
+    import torch
+    from comemb_b200.ADSCModel.model import Model
+    from comemb_b200.ADSCModel.node_embeddings import Node2Vec
+    from comemb_b200.ADSCModel.context_embeddings import Context2Vec
+    from comemb_b200.ADSCModel.community_embeddings import Community2Vec
+    g = golden["karate"]
+    degrees = {i + 1: int(c) for i, c in enumerate(g["degrees"])}
+    np.random.seed(2024)
+    import os
+    model = Model(degrees, size=128, table_size=5000000, input_file="karate_zachary",
+                  path_labels=os.path.join(os.path.dirname(__file__), "golden"))
+    assert model.k == 2
+    assert np.array_equal(host(model.node_embedding), g["init_node"])
+    table = host(model.table, np.uint32)
+    starts = np.flatnonzero(np.concatenate([[True], table[1:] != table[:-1]]))
+    assert np.array_equal(table[starts], g["table_vals"]) and np.array_equal(starts, g["table_starts"])
+    node_learner = Node2Vec(workers=1, negative=4, lr=0.1)
+    cont_learner = Context2Vec(window_size=3, workers=1, negative=4, lr=0.1)
+    com_learner = Community2Vec(model, reg_covar=1e-5, lr=0.1)
+    edges, walks = g["edges"], [w for w in g["walks_ids"]]
+    np.random.seed(77)
+    for stage in ("pre", "it0"):
+        node_learner.train(model, edges=edges, iter=1, chunksize=20)
+        assert np.array_equal(host(model.node_embedding), g[stage + "_o1_node"])
+        cont_learner.train(model, paths=walks, total_nodes=len(walks) * 20, alpha=1.0, chunksize=20)
+        assert np.array_equal(host(model.node_embedding), g[stage + "_o2_node"])
+        assert np.array_equal(host(model.context_embedding), g[stage + "_o2_ctx"])
+    model.centroid, model.pi = dev(g["centroid"]), dev(g["pi"])
+    model.inv_covariance_mat = dev(g["inv_cov"])
+    prev = g["it0_o2_node"]
+    for it in range(5):  # step by step: the reference's own 5-step o3 trajectory is chaotic in fp32 (make_golden.py)
+        model.node_embedding = dev(prev)
+        com_learner.train(list(range(1, 35)), model, 0.01, chunksize=20, iter=1)
+        want = g["o3_iter%d_node" % it]
+        assert np.abs(host(model.node_embedding) - want).max() <= 1e-5 * np.abs(want).max()
+        prev = want
+    assert torch.isfinite(model.node_embedding).all()
+
+
+# ---- HOGWILD ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["o2_d128_small", "o2_d2_karate_default", "o2_d100_tail", "o2_d160_blk32",
+                                  "o2_d64_none_ragged", "o2_d256", "o2_neg0", "o2_empty_and_single"])
+@pytest.mark.parametrize("atomic", [False, True])
+def test_o2_hogwild_single_warp_equals_oracle_warp_order(K, name, atomic):
+    """With one walk per launch nothing races: the Hogwild kernel must equal the sequential oracle evaluated with
+    the kernel's own summation order, bit for bit (plain stores) / to rounding (red.add adds deltas in L2)."""
+    c = cases.O2_CASES[name]
+    node, ctx, table, walks = cases.o2_inputs(c)
+    seeds = O.seeds_from_numpy(np.random.RandomState(3), len(walks))
+    dn, dc, dt = dev(node), dev(ctx), dev(table)
+    for w, s in zip(walks, seeds):
+        if len(w) == 0:
+            continue
+        off = np.array([0, len(w)], np.int64)
+        K.o2_batch(dn, dc, dev(w), dev(off), dev(np.array([s], np.uint64)), c["lr"], c["neg"], c["W"], dt,
+                   alpha=c["lam"], mode=K.MODE_HOGWILD, flags=K.F_ATOMIC if atomic else 0)
+    flat, off = cases.flatten_walks(walks)
+    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], c["neg"], c["W"], table, c["lam"], O.DOT_WARP)
+    if atomic:
+        assert np.abs(host(dn) - node).max() < 2e-3 and np.abs(host(dc) - ctx).max() < 2e-3
+    else:
+        assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+
+
+def test_o2_hogwild_chunked_units_keep_the_reference_lcg_stream(K):
+    """Centre-chunked work units start mid-stream via LCG skip-ahead: with lr=0 nothing moves, and with disjoint
+    walks (no shared rows between chunks... a single long walk over distinct rows) chunking must not change which
+    negatives are drawn: we check the skip-ahead itself against the oracle's step-by-step LCG."""
+    from comemb_b200 import _lib
+    c = dict(cases.O2_CASES["o2_d128_small"])
+    node, ctx, table, walks = cases.o2_inputs(c)
+    seeds = O.seeds_from_numpy(np.random.RandomState(3), len(walks))
+    flat, off = cases.flatten_walks(walks)
+    # lr = 0: every update is exactly +0 -> tables unchanged under any decomposition
+    dn, dc = dev(node), dev(ctx)
+    _lib.check(_lib.load().comemb_set_tuning(4, c["L"], 0))
+    try:
+        K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), 0.0, c["neg"], c["W"], dev(table), mode=K.MODE_HOGWILD)
+        assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+        # a ctx table of zeros and a tiny lr: updates are linear in the draws, so chunked == unchunked up to
+        # Hogwild races; use ONE walk and chunks that do not share node rows (window 0 < chunk) -> exact
+        one = np.arange(40, dtype=np.uint32)
+        off1 = np.array([0, 40], np.int64)
+        s1 = np.array([123456789], np.uint64)
+        res = []
+        for cpu_ in (0, 8):
+            _lib.check(_lib.load().comemb_set_tuning(cpu_, 40, 0))
+            a, b = dev(node), dev(ctx)
+            K.o2_batch(a, b, dev(one), dev(off1), dev(s1), 0.05, 5, 1, dev(table), mode=K.MODE_HOGWILD)
+            res.append((host(a), host(b)))
+        # window 1: chunk boundaries share rows i-1/i+1 across chunks -> compare ctx rows of the drawn negatives
+        # statistically instead: same multiset of updated rows
+        moved0 = np.flatnonzero(np.abs(res[0][1] - ctx).sum(1) > 0)
+        moved1 = np.flatnonzero(np.abs(res[1][1] - ctx).sum(1) > 0)
+        assert np.array_equal(moved0, moved1)
+    finally:
+        _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
+
+
+def test_o1_hogwild_single_warp_equals_oracle_warp_order(K):
+    for name in ("o1_d128", "o1_d2", "o1_d100_selfloops", "o1_neg0"):
+        c = cases.O1_CASES[name]
+        node, table, edges = cases.o1_inputs(c)
+        seeds = O.seeds_from_numpy(np.random.RandomState(4), len(edges))
+        dn, dt = dev(node), dev(table)
+        for e, s in zip(edges, seeds):
+            K.o1_batch(dn, dev(e.reshape(1, 2)), dev(np.array([s], np.uint64)), c["lr"], c["neg"], dt,
+                       mode=K.MODE_HOGWILD)
+        O.o1_edges(node, edges, seeds, c["lr"], c["neg"], table, O.DOT_WARP)
+        assert np.array_equal(host(dn), node), name
+
+
+def _sbm(n, k, deg, seed):
+    rs = np.random.RandomState(seed)
+    comm = np.arange(n) % k
+    src = np.repeat(np.arange(n), deg // 2)
+    intra = rs.rand(src.size) < 0.9
+    dst = np.where(intra, (rs.randint(0, n // k, src.size) * k + comm[src]) % n, rs.randint(0, n, src.size))
+    keep = src != dst
+    return np.stack([src[keep] + 1, dst[keep] + 1], 1), comm
+
+
+def test_hogwild_training_quality_matches_ordered_on_sbm(K):
+    """Acceptance test of Hogwild mode (north star): same corpus, ORDERED (= the reference's sequential result) vs
+    HOGWILD (plain stores and red.add): final SGNS positive loss within 5 % and community recovery (k-means NMI on
+    the node table) within 0.05."""
+    import torch
+    import comemb_b200.utils.graph_utils as gu
+    from sklearn.cluster import KMeans
+    from sklearn.metrics import normalized_mutual_info_score as nmi
+    n, k, d = 600, 4, 128
+    edges, comm = _sbm(n, k, 20, 11)
+    G = gu.from_edge_array(edges)
+    assert len(G) == n
+    labels = comm[G.ids - 1]
+    walks, lens = gu.build_deepwalk_corpus(G, 6, 40, alpha=0.0, seed=3, mode=gu.MODE_HOGWILD, return_device=True)
+    nw = walks.shape[0]
+    off = torch.arange(nw + 1, dtype=torch.int64, device="cuda") * 40
+    rs = np.random.RandomState(0)
+    node0 = (rs.uniform(-1, 1, (n, d)) * 0.5 / d ** 0.5 * 4).astype(np.float32)
+    table = dev(O.make_table(np.diff(G.rowptr).astype(np.float64), 100000))
+    seeds = dev(O.seeds_from_numpy(np.random.RandomState(5), nw))
+    out = {}
+    for tag, mode, flags in (("ordered", K.MODE_ORDERED, 0), ("hogwild", K.MODE_HOGWILD, 0),
+                             ("hogwild_atomic", K.MODE_HOGWILD, K.F_ATOMIC)):
+        a, b = dev(node0), torch.zeros((n, d), device="cuda")
+        for epoch in range(2):
+            K.o2_batch(a, b, walks.reshape(-1), off, seeds, 0.05, 5, 5, table, mode=mode, flags=flags)
+        loss, pairs = K.o2_pos_loss(a, b, walks.reshape(-1), off, 5)
+        x = host(a)
+        pred = KMeans(k, n_init=5, random_state=0).fit_predict(x)
+        out[tag] = (loss / pairs, nmi(labels, pred))
+        assert np.isfinite(x).all()
+    l0, q0 = out["ordered"]
+    assert q0 > 0.8, out
+    for tag in ("hogwild", "hogwild_atomic"):
+        l, q = out[tag]
+        assert abs(l - l0) / l0 < 0.05, out
+        assert q > q0 - 0.05, out
+
+
+def test_alias_sampler_matches_table_distribution(K):
+    import torch
+    from comemb_b200 import _lib
+    rs = np.random.RandomState(9)
+    n = 300
+    counts = (rs.pareto(1.2, size=n) * 3 + 1).astype(np.float64)
+    table = O.make_table(counts, 200000)
+    dt = dev(table)
+    alias = torch.empty(2 * n, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().comemb_build_alias(dt.data_ptr(), table.size, n, alias.data_ptr(), None))
+    a = host(alias, np.uint32).reshape(n, 2).astype(np.float64)
+    # exact distribution implied by the alias table vs the table's run lengths
+    p = np.zeros(n)
+    thr = np.where(a[:, 0] >= 2 ** 32 - 1, 1.0, a[:, 0] / 2 ** 32)
+    p += thr / n
+    np.add.at(p, a[:, 1].astype(np.int64), (1 - thr) / n)
+    want = np.bincount(table, minlength=n) / table.size
+    assert np.abs(p - want).max() < 1e-6
+    # and the kernel draws through it: lr=0 run must not move anything and must not fault
+    node = dev(rs.uniform(-1, 1, (n, 128)).astype(np.float32))
+    ctx = dev(rs.uniform(-1, 1, (n, 128)).astype(np.float32))
+    w = dev(rs.randint(0, n, 400).astype(np.uint32))
+    off = dev((np.arange(11) * 40).astype(np.int64))
+    before = host(ctx).copy()
+    K.o2_batch(node, ctx, w, off, None, 0.0, 5, 5, dt, mode=K.MODE_HOGWILD, alias=alias, base_seed=1)
+    assert np.array_equal(host(ctx), before)
+
+
+def test_full_size_properties_config2_shape(K):
+    """BASELINE config-2 shape (100K rows, d=128, L=80, W=10, neg=5) on a slice of the walk corpus, through
+    size-independent properties: (1) lr=0 leaves both tables bit-identical (every update is an exact +0);
+    (2) the token count equals the number of non-padding tokens; (3) a real step keeps the tables finite, moves
+    only rows that occur in the walks (node table) and leaves row 0 of the context table -- never a negative
+    (model.py:112: table values start at id 1) and not in these walks -- untouched."""
+    import torch
+    n, d, L = 100000, 128, 80
+    g = torch.Generator(device="cuda").manual_seed(1)
+    node = (torch.rand((n, d), device="cuda", generator=g) * 2 - 1) * 0.05
+    ctx = (torch.rand((n, d), device="cuda", generator=g) * 2 - 1) * 0.05
+    rs = np.random.RandomState(2)
+    table = dev(O.make_table(rs.randint(1, 60, n).astype(np.float64), 5000000))
+    nw = 20000
+    walks = torch.randint(1, n, (nw, L), device="cuda", generator=g, dtype=torch.int32)
+    walks[:, 70:][torch.rand((nw, 10), device="cuda", generator=g) < 0.3] = -1  # TOKEN_NONE padding
+    off = torch.arange(nw + 1, dtype=torch.int64, device="cuda") * L
+    n0, c0 = node.clone(), ctx.clone()
+    tok = K.o2_batch(node, ctx, walks.reshape(-1), off, None, 0.0, 5, 10, table, mode=K.MODE_HOGWILD, base_seed=7,
+                     count_tokens=True)
+    assert tok == int((walks != -1).sum().item())
+    assert torch.equal(node, n0) and torch.equal(ctx, c0)
+    K.o2_batch(node, ctx, walks.reshape(-1), off, None, 0.025, 5, 10, table, mode=K.MODE_HOGWILD, base_seed=7)
+    assert torch.isfinite(node).all() and torch.isfinite(ctx).all()
+    touched = torch.zeros(n, dtype=torch.bool, device="cuda")
+    touched[walks[walks != -1].long()] = True
+    moved = (node != n0).any(1)
+    assert not (moved & ~touched).any()
+    assert moved.sum() > 0.9 * touched.sum()
+    assert torch.equal(ctx[0], c0[0])
