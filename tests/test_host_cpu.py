@@ -1,0 +1,159 @@
+"""CPU-only tests (no CUDA call): the C-ABI library loads and exports every declared symbol, the host-side mirror of
+the reference interface behaves like the reference's Python, and the product never touches oracle/."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "nodeembedding-to-communityembedding_b200")
+
+
+def test_capi_exports_every_declared_symbol():
+    from comemb_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "comemb_b200.h")).read()
+    declared = set(re.findall(r"\b(comemb_[a-z0-9_]+)\s*\(", header))
+    assert {"comemb_init", "comemb_o2_walks", "comemb_o1_edges", "comemb_o3_batch", "comemb_sg_fused",
+            "comemb_walks_csr", "comemb_make_table"} <= declared
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.comemb_abi_version() == 1
+    assert b"invalid argument" in lib.comemb_error_string(-1)
+
+
+def test_product_never_imports_the_oracle():
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "libcomemb_oracle" not in src, f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from comemb_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libcomemb_b200.so")
+    with pytest.raises(_lib.ComembError):
+        _lib.load()
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only box")
+    import comemb_b200.utils.training_sdg_inner as K
+    node = np.zeros((4, 8), np.float32)
+    with pytest.raises(Exception):
+        K.train_o2(node, node.copy(), [O.RefVocab(0), O.RefVocab(1)], 0.1, 1, 1, np.ones(4, np.uint32), py_size=8)
+
+
+def test_draw_seeds_equals_the_reference_expression():
+    import comemb_b200.utils.training_sdg_inner as K
+    np.random.seed(5)
+    want = [(2 ** 24) * np.random.randint(0, 2 ** 24) + np.random.randint(0, 2 ** 24) for _ in range(50)]  # pyx:477
+    np.random.seed(5)
+    got = K.draw_seeds(50)
+    assert got.dtype == np.uint64 and got.tolist() == want
+
+
+class _M(object):
+    pass
+
+
+def _model(ids, probs=None):
+    from comemb_b200.utils.embedding import Vocab
+    m = _M()
+    m.vocab = {}
+    for i, node in enumerate(sorted(ids)):
+        m.vocab[node] = Vocab(index=i, count=1, sample_probability=1.0 if probs is None else probs[i])
+    from comemb_b200.ADSCModel.model import Model
+    m._id_index = None
+    m.id_index = lambda: Model.id_index(m)
+    return m
+
+
+def test_paths_to_rows_matches_prepare_sentences():
+    from comemb_b200.utils.embedding import paths_to_rows, prepare_sentences, chunkize_serial, RepeatCorpusNTimes
+    m = _model([1, 2, 3, 5, 8, 13])
+    paths = [np.array([1, 2, 99, 5]), [13, 13, 4], [], np.array([8])]
+    flat, off = paths_to_rows(m, paths)
+    ref = [[v.index for v in p] for p in prepare_sentences(m, paths)]
+    assert [flat[off[i]:off[i + 1]].tolist() for i in range(len(paths))] == ref == [[0, 1, 3], [5, 5], [], [4]]
+    # down-sampling consumes np.random.random_sample() in the same order
+    probs = [1.0, 0.5, 1.0, 0.2, 1.0, 0.7]
+    m = _model([1, 2, 3, 5, 8, 13], probs)
+    big = [np.random.RandomState(1).choice([1, 2, 3, 5, 8, 13, 77], size=200)]
+    np.random.seed(3)
+    ref = [[v.index for v in p] for p in prepare_sentences(m, big)]
+    np.random.seed(3)
+    flat, off = paths_to_rows(m, big)
+    assert flat.tolist() == ref[0]
+    assert list(chunkize_serial(range(7), 3)) == [[0, 1, 2], [3, 4, 5], [6]]
+    assert list(RepeatCorpusNTimes([1, 2], 2)) == [1, 2, 1, 2]
+
+
+def test_graph_from_karate_file_reproduces_the_reference_graph(golden):
+    """Row order, neighbour order and edge order of the networkx graph the reference builds (golden CSR extracted
+    from its own graph object, make_golden.py) -- needed for bit-exact ORDERED walks from a file."""
+    import comemb_b200.utils.graph_utils as gu
+    G = gu.load_adjacencylist(os.path.join(ROOT, "tests", "golden", "karate.adjlist"), True)
+    g = golden["walks"]
+    assert np.array_equal(G.ids, g["karate/ids"])
+    assert np.array_equal(G.rowptr, g["karate/rowptr"])
+    assert np.array_equal(G.col, g["karate/col"])
+    assert np.array_equal(G.edges(), golden["karate"]["edges"])
+    assert G.number_of_nodes() == 34 and G.number_of_edges() == 78
+    deg = G.degree()
+    assert [deg[i] for i in sorted(deg)] == golden["karate"]["degrees"].tolist()
+    assert gu.file_seed(random.Random(9999999999)) == 102045471  # adsc_Karate.py:79 -> graph_utils.py:150
+
+
+def test_fast_csr_and_sbm_builder():
+    import comemb_b200.utils.graph_utils as gu
+    G, block = gu.sbm_graph(2000, 10, 20, seed=1)
+    assert len(G) == 2000 and G.rowptr[-1] == G.col.size
+    src = np.repeat(np.arange(2000), np.diff(G.rowptr))
+    assert (src != G.col).all()                                   # no self loops
+    key = src.astype(np.int64) * 2000 + G.col
+    assert np.unique(key).size == key.size                        # no duplicates
+    assert set(zip(src.tolist(), G.col.tolist())) == set(zip(G.col.tolist(), src.tolist()))  # symmetric
+    intra = (block[src] == block[G.col]).mean()
+    assert 0.7 < intra < 0.9
+
+
+def test_io_utils_roundtrip(tmp_path):
+    from comemb_b200.utils.IO_utils import load_embedding, load_ground_true, save_embedding
+    emb = np.random.RandomState(0).rand(5, 3).astype(np.float32)
+    save_embedding(emb, "e", path=str(tmp_path))
+    first = open(os.path.join(str(tmp_path), "e.txt")).readline()
+    assert first.startswith("1\t") and len(first.split("\t")[1].split(" ")) == 3
+    assert np.allclose(load_embedding("e", path=str(tmp_path)), emb)
+    labels, k = load_ground_true(os.path.join(ROOT, "tests", "golden"), "karate_zachary")
+    assert len(labels) == 34 and k == 2
+
+
+def test_pairs_per_walk_formula():
+    import bench
+    assert bench.pairs_of_len(80, 10) == 1490
+    assert bench.pairs_of_len(1, 10) == 0 and bench.pairs_of_len(3, 2) == 6
+    assert bench.B_PAIR == 7168
+
+
+def test_oracle_lcg_skip_matches_closed_form():
+    # the device skip-ahead composes affine maps; the same algebra in python ints against the oracle's stepping
+    a, c, mask = 25214903917, 11, (1 << 48) - 1
+    for x0, n in ((123456789, 0), (1, 1), (987654321012, 7450), (2 ** 47 + 5, 12345)):
+        A, C, aa, cc, k = 1, 0, a, c, n
+        while k:
+            if k & 1:
+                A, C = (A * aa) & mask, (C * aa + cc) & mask
+            cc, aa = ((aa + 1) * cc) & mask, (aa * aa) & mask
+            k >>= 1
+        assert (A * x0 + C) & mask == O.lcg_advance(x0, n)
