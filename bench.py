@@ -229,6 +229,8 @@ def run_ours(args):
     from comemb_b200 import _lib, replicas
     K.init()
     flags = K.F_ATOMIC if args.atomic else 0
+    if args.tuning:
+        _lib.check(_lib.load().comemb_set_tuning(*args.tuning))
 
     G, _ = build_workload()
     n, d, L, W, neg, lr = CFG["n"], CFG["d"], CFG["L"], CFG["W"], CFG["neg"], CFG["lr"]
@@ -373,6 +375,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--atomic", type=int, default=0, help="1: scatter with red.global.add.v4.f32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tuning", type=int, nargs=3, default=None, metavar=("CENTRES", "MAXLEN", "BLOCKS"),
+                    help="comemb_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm) for experiments")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

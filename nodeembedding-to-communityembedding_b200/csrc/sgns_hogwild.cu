@@ -22,6 +22,7 @@ struct Tuning {
     int centres_per_unit = 0;  // 0 = a whole walk per warp
     int max_walk_len = 0;      // needed when centres_per_unit > 0
     int blocks_per_sm = 0;     // 0 = occupancy query
+    int variant = 0;           // d=128 o2 kernel: 3 -> 80-register build (3 CTAs/SM), else 64-register build (4 CTAs/SM)
 };
 Tuning g_tuning;
 
@@ -149,13 +150,40 @@ struct O2Params {
     const float *glut;
 };
 
-template <int NCH, bool VEC, bool ATOMIC>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) o2_hogwild_kernel(const O2Params P) {
+// 8-slot transposed warp reduction.  Slot sums are formed by exactly the same lane pairings, level by level
+// (xor 16, 8, 4, 2, 1), as eight independent xor-butterflies would use -- so every slot total is bit-identical to
+// warp_sum_xor() of that slot -- but each level halves the number of live slots: 9 shuffles instead of 40.
+// On return lane l holds the total of slot (l >> 2) & 7.
+__device__ __forceinline__ float reduce8_transposed(float p0, float p1, float p2, float p3, float p4, float p5,
+                                                    float p6, float p7, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const float q0 = (b4 ? p4 : p0) + __shfl_xor_sync(FULL, b4 ? p0 : p4, 16);
+    const float q1 = (b4 ? p5 : p1) + __shfl_xor_sync(FULL, b4 ? p1 : p5, 16);
+    const float q2 = (b4 ? p6 : p2) + __shfl_xor_sync(FULL, b4 ? p2 : p6, 16);
+    const float q3 = (b4 ? p7 : p3) + __shfl_xor_sync(FULL, b4 ? p3 : p7, 16);
+    const float r0 = (b3 ? q2 : q0) + __shfl_xor_sync(FULL, b3 ? q0 : q2, 8);
+    const float r1 = (b3 ? q3 : q1) + __shfl_xor_sync(FULL, b3 ? q1 : q3, 8);
+    float t = (b2 ? r1 : r0) + __shfl_xor_sync(FULL, b2 ? r0 : r1, 4);
+    t += __shfl_xor_sync(FULL, t, 2);
+    t += __shfl_xor_sync(FULL, t, 1);
+    return t;
+}
+
+// p_i ends on the four lanes whose bits (b4,b3,b2) spell i: level 16 keeps by i>>2, level 8 by (i>>1)&1, level 4 by i&1
+__host__ __device__ constexpr int lane_of_p(int i) {
+    return ((i >> 2) << 4) | (((i >> 1) & 1) << 3) | ((i & 1) << 2);
+}
+
+template <int NCH, bool VEC, bool ATOMIC, int DFIX, int MINB = 1>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_kernel(const O2Params P) {
     __shared__ float lut[EXP_TABLE_SIZE];
     for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int d = P.d, W = P.window, negative = P.negative;
+    const int d = DFIX ? DFIX : P.d;
+    const int W = P.window, negative = P.negative;
+    const float lr = P.lr, lambda = P.lambda;
+    float *const node = P.node, *const ctx = P.ctx;
     const int64_t n_units = P.n_walks * P.units_per_walk;
     const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
@@ -189,28 +217,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) o2_hogwild_kernel(const 
         for (int i = c0; i < c1; i++) {  // pyx:494
             const uint32_t wi = __ldg(path + i);
             if (wi == COMEMB_TOKEN_NONE) continue;
-            float *pos_ptr = P.ctx + (int64_t)wi * d;
+            float *pos_ptr = ctx + (int64_t)wi * d;
             Row<NCH> cpos = row_load<NCH, VEC>(pos_ptr, d, lane);
             Row<NCH> dpos = row_zero<NCH>();  // ATOMIC: accumulated delta of the positive row
             const int j1 = min(len, i + W + 1);
             for (int j = max(0, i - W); j < j1; j++) {  // pyx:503
                 const uint32_t wj = __ldg(path + j);
                 if (j == i || wj == COMEMB_TOKEN_NONE) continue;
-                float *row1_ptr = P.node + (int64_t)wj * d;
+                float *row1_ptr = node + (int64_t)wj * d;
                 const Row<NCH> row1 = row_load<NCH, VEC>(row1_ptr, d, lane);
                 Row<NCH> work = row_zero<NCH>();
-                // positive target (label 1), pyx:129-131
-                {
-                    const float f = warp_sum_xor(dot_part<NCH>(row1, cpos));
-                    if (f > -MAX_EXP_F && f < MAX_EXP_F) {
-                        const float g = sgns_g(f, 1.f, P.lr, P.lambda, lut);
-                        row_fma<NCH>(work, g, cpos);  // pyx:146
-                        if (ATOMIC) row_fma<NCH>(dpos, g, row1);
-                        row_fma<NCH>(cpos, g, row1);  // pyx:147 (kept in registers)
-                    }
-                }
-                for (int kb = 0; kb < negative; kb += NEGB) {
-                    const int nb = min(NEGB, negative - kb);
+                bool pos_done = false;
+                for (int kb = 0; kb < negative || !pos_done; kb += NEGB) {
+                    const int nb = max(0, min(NEGB, negative - kb));
                     // draw nb negatives: every lane steps the LCG, lane k fetches sample k (pyx:133-134)
                     uint64_t mine = 0;
 #pragma unroll
@@ -219,40 +238,67 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) o2_hogwild_kernel(const 
                             if (lane == k) mine = rnd;
                             rnd = lcg_next(rnd);
                         }
-                    uint32_t tmine = (lane < nb) ? draw_fetch(P.draw, mine) : 0u;
+                    const uint32_t tmine = (lane < nb) ? draw_fetch(P.draw, mine) : wi;
                     uint32_t t[NEGB];
-                    bool act[NEGB];
                     Row<NCH> c[NEGB];
+                    unsigned actmask = pos_done ? 0u : 1u;  // bit 0 = the positive target (first batch only)
 #pragma unroll
                     for (int k = 0; k < NEGB; k++) {
                         t[k] = __shfl_sync(FULL, tmine, k);
-                        act[k] = (k < nb) && (t[k] != wi);  // pyx:135-136
-                        if (act[k]) c[k] = row_load<NCH, VEC>(P.ctx + (int64_t)t[k] * d, d, lane);
+                        const bool a = (k < nb) && (t[k] != wi);  // pyx:135-136
+                        if (a) {
+                            actmask |= 2u << k;
+                            c[k] = row_load<NCH, VEC>(ctx + (int64_t)t[k] * d, d, lane);
+                        } else {
+                            c[k] = row_zero<NCH>();
+                        }
                     }
-                    float f[NEGB];
+                    // an earlier sample of this batch hitting the same row must be seen by the later one
+                    unsigned dupmask = 0;
 #pragma unroll
-                    for (int k = 0; k < NEGB; k++) f[k] = act[k] ? dot_part<NCH>(row1, c[k]) : 0.f;
-#pragma unroll
-                    for (int k = 0; k < NEGB; k++) f[k] = warp_sum_xor(f[k]);
-#pragma unroll
-                    for (int k = 0; k < NEGB; k++) {
-                        if (!act[k]) continue;
-                        bool dup = false;  // an earlier sample of this batch hit the same row: it must see that update
+                    for (int k = 1; k < NEGB; k++)
 #pragma unroll
                         for (int a = 0; a < k; a++)
-                            if (act[a] && t[a] == t[k]) {
-                                c[k] = c[a];
-                                dup = true;
-                            }
-                        float fk = f[k];
-                        if (dup) fk = warp_sum_xor(dot_part<NCH>(row1, c[k]));
-                        if (fk <= -MAX_EXP_F || fk >= MAX_EXP_F) continue;  // pyx:141-142
-                        const float g = sgns_g(fk, 0.f, P.lr, P.lambda, lut);
+                            if (t[a] == t[k] && ((actmask >> (k + 1)) & (actmask >> (a + 1)) & 1u)) dupmask |= 1u << k;
+                    // all dots of the batch at once: positive in slot 0, negative k in p_{k+1}
+                    const float p0 = pos_done ? 0.f : dot_part<NCH>(row1, cpos);
+                    const float fm = reduce8_transposed(p0, dot_part<NCH>(row1, c[0]), dot_part<NCH>(row1, c[1]),
+                                                        dot_part<NCH>(row1, c[2]), dot_part<NCH>(row1, c[3]),
+                                                        dot_part<NCH>(row1, c[4]), 0.f, 0.f, lane);
+                    // this lane's slot holds p_i with lane_of_p(i) == (lane & 28): i = (b4<<2)|(b3<<1)|b2
+                    const int pi = ((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1);
+                    float gm = 0.f;
+                    if (((actmask >> pi) & 1u) && fm > -MAX_EXP_F && fm < MAX_EXP_F)
+                        gm = sgns_g(fm, pi == 0 ? 1.f : 0.f, lr, lambda, lut);  // pyx:141-144
+                    if (!pos_done) {  // positive target (label 1), pyx:129-131
+                        const float g = __shfl_sync(FULL, gm, lane_of_p(0));
+                        if (g != 0.f) {
+                            row_fma<NCH>(work, g, cpos);  // pyx:146
+                            if (ATOMIC) row_fma<NCH>(dpos, g, row1);
+                            row_fma<NCH>(cpos, g, row1);  // pyx:147 (kept in registers)
+                        }
+                        pos_done = true;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NEGB; k++) {
+                        float g = __shfl_sync(FULL, gm, lane_of_p(k + 1));
+                        if (dupmask & (1u << k)) {  // rare: redo this target against the refreshed row
+#pragma unroll
+                            for (int a = 0; a < k; a++)
+                                if (t[a] == t[k] && ((actmask >> (a + 1)) & 1u)) c[k] = c[a];
+                            const float fk = warp_sum_xor(dot_part<NCH>(row1, c[k]));
+                            g = (fk > -MAX_EXP_F && fk < MAX_EXP_F) ? sgns_g(fk, 0.f, lr, lambda, lut) : 0.f;
+                        }
+                        if (g == 0.f) continue;  // inactive, skipped (pyx:135-136, 141-142) -- sigma is never 0 or 1
                         row_fma<NCH>(work, g, c[k]);  // pyx:146
-                        float *cp = P.ctx + (int64_t)t[k] * d;
-                        if (ATOMIC) row_red<NCH, VEC>(cp, row_scaled<NCH>(g, row1), d, lane);
-                        row_fma<NCH>(c[k], g, row1);  // pyx:147
-                        if (!ATOMIC) row_store<NCH, VEC>(cp, c[k], d, lane);
+                        float *cp = ctx + (int64_t)t[k] * d;
+                        if (ATOMIC) {
+                            row_red<NCH, VEC>(cp, row_scaled<NCH>(g, row1), d, lane);
+                            if (dupmask) row_fma<NCH>(c[k], g, row1);
+                        } else {
+                            row_fma<NCH>(c[k], g, row1);  // pyx:147
+                            row_store<NCH, VEC>(cp, c[k], d, lane);
+                        }
                     }
                 }
                 // pyx:149
@@ -269,6 +315,207 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) o2_hogwild_kernel(const 
                 row_red<NCH, VEC>(pos_ptr, dpos, d, lane);
             else
                 row_store<NCH, VEC>(pos_ptr, cpos, d, lane);
+        }
+    }
+}
+
+// ---- o2, headline shape: size == 128 (one float4 per lane), NEG negatives known at compile time ----------------------------
+// Same semantics as o2_hogwild_kernel, leaner instruction stream:
+//   * lane k < NEG jumps straight to its own LCG state (affine skip constants A_k, C_k), every lane then advances the
+//     walk's state by NEG steps with one multiply-add;  the NEXT pair's table lookups are issued one pair ahead;
+//   * all NEG+1 rows are loaded unconditionally (a dropped sample just gets g = 0), no per-row predicate moves;
+//   * one transposed reduction + one lane-parallel sigma evaluation per pair;
+//   * duplicate samples inside a pair (which must see each other's update, pyx:146-147) are detected with one
+//     match.any and handled by a sequential path that re-reads rows from memory.
+template <int NEG>
+struct LcgJump {  // x_{n+k} = A_k x_n + C_k  (mod 2^48)
+    uint64_t A[NEG + 1], C[NEG + 1];
+    __host__ __device__ constexpr LcgJump() : A{}, C{} {
+        uint64_t a = 1, c = 0;
+        for (int k = 0; k <= NEG; k++) {
+            A[k] = a & LCG_MASK;
+            C[k] = c & LCG_MASK;
+            c = (c * LCG_MUL + 11ULL) & LCG_MASK;
+            a = (a * LCG_MUL) & LCG_MASK;
+        }
+    }
+};
+
+template <bool ATOMIC, int NEG, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_kernel(const O2Params P) {
+    static_assert(NEG >= 1 && NEG <= 7, "positive + negatives must fit the 8 reduction slots");
+    constexpr int D = 128;
+    constexpr LcgJump<NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int W = P.window;
+    const float lr = P.lr, lambda = P.lambda;
+    float *const node_l = P.node + 4 * lane, *const ctx_l = P.ctx + 4 * lane;  // this lane's float4 column
+    const Draw draw = P.draw;
+    // this lane's jump constants (lanes >= NEG never use theirs)
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    // slot i of reduce8_transposed ends on lanes with (b4,b3,b2) == i; label 1 only for slot 0 (the positive)
+    const int pi = ((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1);
+    const float my_label = pi == 0 ? 1.f : 0.f;
+    const int64_t n_units = P.n_walks * P.units_per_walk;
+    const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+
+    for (int64_t u = warp0; u < n_units; u += n_warps) {
+        const int64_t w = u / P.units_per_walk;
+        const int q = (int)(u - w * P.units_per_walk);
+        const uint32_t *path = P.walks + P.walk_off[w];
+        const int len = (int)min((int64_t)MAX_SENTENCE_LEN, P.walk_off[w + 1] - P.walk_off[w]);  // pyx:480
+        const int c0 = P.centres_per_unit ? q * P.centres_per_unit : 0;
+        const int c1 = P.centres_per_unit ? min(len, c0 + P.centres_per_unit) : len;
+        if (c0 >= len) continue;
+        uint64_t rnd = P.seeds ? P.seeds[w] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        if (q == 0 && P.n_tokens) {  // train_o2's return value (pyx:490)
+            int cnt = 0;
+            for (int i = lane; i < len; i += 32) cnt += (__ldg(path + i) != COMEMB_TOKEN_NONE);
+            cnt = __reduce_add_sync(FULL, cnt);
+            if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(P.n_tokens), (unsigned long long)cnt);
+        }
+        if (c0 > 0) {
+            int pairs = 0;
+            for (int i = lane; i < c0; i += 32) {
+                if (__ldg(path + i) == COMEMB_TOKEN_NONE) continue;
+                const int j1 = min(len, i + W + 1);
+                for (int j = max(0, i - W); j < j1; j++) pairs += (j != i && __ldg(path + j) != COMEMB_TOKEN_NONE);
+            }
+            pairs = __reduce_add_sync(FULL, pairs);
+            rnd = lcg_skip(rnd, (uint64_t)pairs * (uint64_t)NEG);
+        }
+        // samples of the NEXT pair to run, fetched one pair ahead (the draw depends only on the LCG stream, which
+        // advances by exactly NEG per pair whatever the pair turns out to be)
+        uint32_t tnext = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
+        rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+
+        for (int i = c0; i < c1; i++) {  // pyx:494
+            const uint32_t wi = __ldg(path + i);
+            if (wi == COMEMB_TOKEN_NONE) continue;
+            float *pos_ptr = ctx_l + (int64_t)wi * D;
+            float4 cpos = __ldcg(reinterpret_cast<const float4 *>(pos_ptr));
+            float4 dpos = make_float4(0.f, 0.f, 0.f, 0.f);  // ATOMIC: accumulated delta of the positive row
+            const int j1 = min(len, i + W + 1);
+            for (int j = max(0, i - W); j < j1; j++) {  // pyx:503
+                const uint32_t wj = __ldg(path + j);
+                if (j == i || wj == COMEMB_TOKEN_NONE) continue;
+                float *row1_ptr = node_l + (int64_t)wj * D;
+                const float4 r1 = __ldcg(reinterpret_cast<const float4 *>(row1_ptr));
+                const uint32_t tmine = tnext;  // this pair's samples (lane k holds sample k)
+                tnext = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
+                rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+                // two equal samples in one pair? (lanes >= NEG carry distinct dummies)
+                const unsigned same = __match_any_sync(FULL, tmine);
+                const bool anydup = __any_sync(FULL, (same & (same - 1)) != 0u);
+                float4 work = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!anydup) {
+                    uint32_t t[NEG];
+                    float4 c[NEG];
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) {
+                        t[k] = __shfl_sync(FULL, tmine, k);
+                        c[k] = __ldcg(reinterpret_cast<const float4 *>(ctx_l + (int64_t)t[k] * D));
+                    }
+                    float p[8];
+                    p[0] = fmaf(r1.w, cpos.w, fmaf(r1.z, cpos.z, fmaf(r1.y, cpos.y, fmaf(r1.x, cpos.x, 0.f))));
+#pragma unroll
+                    for (int k = 0; k < 7; k++)
+                        p[k + 1] = k < NEG ? fmaf(r1.w, c[k < NEG ? k : 0].w,
+                                                  fmaf(r1.z, c[k < NEG ? k : 0].z,
+                                                       fmaf(r1.y, c[k < NEG ? k : 0].y,
+                                                            fmaf(r1.x, c[k < NEG ? k : 0].x, 0.f))))
+                                           : 0.f;
+                    const float fm = reduce8_transposed(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], lane);
+                    // is my slot a live target?  slot 0 always; slot k+1 iff sample k != centre (pyx:135-136)
+                    bool live = pi == 0;
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) live = live || (pi == k + 1 && t[k] != wi);
+                    float gm = 0.f;
+                    if (live && fm > -MAX_EXP_F && fm < MAX_EXP_F)  // pyx:141-144
+                        gm = __fmul_rn(__fmul_rn(my_label - lut[lut_index(fm)], lr), lambda);
+                    {
+                        const float g = __shfl_sync(FULL, gm, lane_of_p(0));
+                        work.x = fmaf(g, cpos.x, work.x); work.y = fmaf(g, cpos.y, work.y);  // pyx:146
+                        work.z = fmaf(g, cpos.z, work.z); work.w = fmaf(g, cpos.w, work.w);
+                        if (ATOMIC) {
+                            dpos.x = fmaf(g, r1.x, dpos.x); dpos.y = fmaf(g, r1.y, dpos.y);
+                            dpos.z = fmaf(g, r1.z, dpos.z); dpos.w = fmaf(g, r1.w, dpos.w);
+                        }
+                        cpos.x = fmaf(g, r1.x, cpos.x); cpos.y = fmaf(g, r1.y, cpos.y);  // pyx:147 (registers)
+                        cpos.z = fmaf(g, r1.z, cpos.z); cpos.w = fmaf(g, r1.w, cpos.w);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) {
+                        const float g = __shfl_sync(FULL, gm, lane_of_p(k + 1));
+                        work.x = fmaf(g, c[k].x, work.x); work.y = fmaf(g, c[k].y, work.y);  // pyx:146
+                        work.z = fmaf(g, c[k].z, work.z); work.w = fmaf(g, c[k].w, work.w);
+                        float *cp = ctx_l + (int64_t)t[k] * D;
+                        if (g != 0.f) {  // g == 0 <=> dropped or saturated target (sigma is never exactly 0 or 1)
+                            if (ATOMIC) {
+                                red_add4(cp, make_float4(__fmul_rn(g, r1.x), __fmul_rn(g, r1.y), __fmul_rn(g, r1.z),
+                                                         __fmul_rn(g, r1.w)));
+                            } else {  // pyx:147
+                                st4(cp, make_float4(fmaf(g, r1.x, c[k].x), fmaf(g, r1.y, c[k].y), fmaf(g, r1.z, c[k].z),
+                                                    fmaf(g, r1.w, c[k].w)));
+                            }
+                        }
+                    }
+                } else {
+                    // sequential path: every target re-reads its row after the previous target's write
+                    {
+                        const float f = warp_sum_xor(
+                            fmaf(r1.w, cpos.w, fmaf(r1.z, cpos.z, fmaf(r1.y, cpos.y, fmaf(r1.x, cpos.x, 0.f)))));
+                        if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+                            const float g = sgns_g(f, 1.f, lr, lambda, lut);
+                            work.x = fmaf(g, cpos.x, work.x); work.y = fmaf(g, cpos.y, work.y);
+                            work.z = fmaf(g, cpos.z, work.z); work.w = fmaf(g, cpos.w, work.w);
+                            if (ATOMIC) {
+                                dpos.x = fmaf(g, r1.x, dpos.x); dpos.y = fmaf(g, r1.y, dpos.y);
+                                dpos.z = fmaf(g, r1.z, dpos.z); dpos.w = fmaf(g, r1.w, dpos.w);
+                            }
+                            cpos.x = fmaf(g, r1.x, cpos.x); cpos.y = fmaf(g, r1.y, cpos.y);
+                            cpos.z = fmaf(g, r1.z, cpos.z); cpos.w = fmaf(g, r1.w, cpos.w);
+                        }
+                    }
+#pragma unroll 1
+                    for (int k = 0; k < NEG; k++) {
+                        const uint32_t tk = __shfl_sync(FULL, tmine, k);
+                        if (tk == wi) continue;  // pyx:135-136
+                        float *cp = ctx_l + (int64_t)tk * D;
+                        const float4 c = __ldcg(reinterpret_cast<const float4 *>(cp));
+                        const float f = warp_sum_xor(fmaf(r1.w, c.w, fmaf(r1.z, c.z, fmaf(r1.y, c.y, fmaf(r1.x, c.x, 0.f)))));
+                        if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;  // pyx:141-142
+                        const float g = sgns_g(f, 0.f, lr, lambda, lut);
+                        work.x = fmaf(g, c.x, work.x); work.y = fmaf(g, c.y, work.y);
+                        work.z = fmaf(g, c.z, work.z); work.w = fmaf(g, c.w, work.w);
+                        if (ATOMIC)
+                            red_add4(cp, make_float4(__fmul_rn(g, r1.x), __fmul_rn(g, r1.y), __fmul_rn(g, r1.z),
+                                                     __fmul_rn(g, r1.w)));
+                        else
+                            st4(cp, make_float4(fmaf(g, r1.x, c.x), fmaf(g, r1.y, c.y), fmaf(g, r1.z, c.z),
+                                                fmaf(g, r1.w, c.w)));
+                    }
+                }
+                // pyx:149
+                if (ATOMIC)
+                    red_add4(row1_ptr, work);
+                else
+                    st4(row1_ptr, make_float4(r1.x + work.x, r1.y + work.y, r1.z + work.z, r1.w + work.w));
+            }
+            if (ATOMIC)
+                red_add4(pos_ptr, dpos);
+            else
+                st4(pos_ptr, cpos);
         }
     }
 }
@@ -389,16 +636,34 @@ int grid_for(K kernel, int64_t n_units) {
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
-template <int NCH, bool VEC>
+template <int NCH, bool VEC, int DFIX = 0, int MINB = 1>
 int launch_o2_t(const O2Params &P, bool atomic, cudaStream_t st) {
     const int64_t n_units = P.n_walks * P.units_per_walk;
     if (atomic) {
-        auto k = o2_hogwild_kernel<NCH, VEC, true>;
+        auto k = o2_hogwild_kernel<NCH, VEC, true, DFIX, MINB>;
         k<<<grid_for(k, n_units), WARPS_PER_BLOCK * 32, 0, st>>>(P);
     } else {
-        auto k = o2_hogwild_kernel<NCH, VEC, false>;
+        auto k = o2_hogwild_kernel<NCH, VEC, false, DFIX, MINB>;
         k<<<grid_for(k, n_units), WARPS_PER_BLOCK * 32, 0, st>>>(P);
     }
+    return (int)cudaGetLastError();
+}
+
+template <int NEG>
+int launch_o2_d128(const O2Params &P, bool atomic, cudaStream_t st) {
+    const int64_t n_units = P.n_walks * P.units_per_walk;
+    const bool small = g_tuning.variant == 4;  // 64-register build (4 CTAs/SM) instead of the default 3 CTAs/SM
+#define COMEMB_LAUNCH(ATOM, MINB)                                            \
+    do {                                                                     \
+        auto k = o2_hogwild_d128_kernel<ATOM, NEG, MINB>;                    \
+        k<<<grid_for(k, n_units), WARPS_PER_BLOCK * 32, 0, st>>>(P);         \
+    } while (0)
+    if (atomic) {
+        if (small) COMEMB_LAUNCH(true, 4); else COMEMB_LAUNCH(true, 3);
+    } else {
+        if (small) COMEMB_LAUNCH(false, 4); else COMEMB_LAUNCH(false, 3);
+    }
+#undef COMEMB_LAUNCH
     return (int)cudaGetLastError();
 }
 
@@ -419,7 +684,8 @@ int launch_o1_t(const O1Params &P, bool atomic, cudaStream_t st) {
 void hogwild_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm) {
     g_tuning.centres_per_unit = centres_per_unit;
     g_tuning.max_walk_len = max_walk_len;
-    g_tuning.blocks_per_sm = blocks_per_sm;
+    g_tuning.blocks_per_sm = blocks_per_sm % 100;
+    g_tuning.variant = blocks_per_sm / 100;  // hundreds digit selects the kernel variant (experiments)
 }
 
 int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, const int64_t *walk_off,
@@ -441,6 +707,14 @@ int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, 
     P.n_tokens = n_tokens;
     P.glut = comemb_lut_device();
     const bool vec = (size % 4) == 0;
+    if (size == 128 && g_tuning.variant != 9) {  // the headline shape (variant 9 forces the generic kernel: tests)
+        switch (negative) {
+            case 3: return launch_o2_d128<3>(P, atomic, st);
+            case 4: return launch_o2_d128<4>(P, atomic, st);
+            case 5: return launch_o2_d128<5>(P, atomic, st);
+            default: break;
+        }
+    }
     if (size <= 128) return vec ? launch_o2_t<1, true>(P, atomic, st) : launch_o2_t<1, false>(P, atomic, st);
     if (size <= 256) return vec ? launch_o2_t<2, true>(P, atomic, st) : launch_o2_t<2, false>(P, atomic, st);
     return vec ? launch_o2_t<4, true>(P, atomic, st) : launch_o2_t<4, false>(P, atomic, st);
