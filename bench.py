@@ -246,6 +246,10 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
     lib = _lib.load()
+    alias = None
+    if args.alias:
+        alias = torch.empty(2 * n, dtype=torch.int32, device="cuda")
+        _lib.check(lib.comemb_build_alias(table.data_ptr(), table.numel(), n, alias.data_ptr(), None))
     pairs_lut = torch.tensor([pairs_of_len(l, W) for l in range(L + 1)], dtype=torch.int64, device="cuda")
 
     def step(s, ev=None):
@@ -256,7 +260,7 @@ def run_ours(args):
         if ev:
             ev[0].record(stream)
         K.o2_batch(node, ctx, walks.reshape(-1), off, None, lr, neg, W, table, mode=K.MODE_HOGWILD, flags=flags,
-                   base_seed=1000003 * s + rank)
+                   alias=alias, base_seed=1000003 * s + rank)
         if ev:
             ev[1].record(stream)
         if world > 1:
@@ -329,7 +333,7 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "o2_hogwild_kernel<1,true,%s>" % ("true" if args.atomic else "false"),
+    roofline = {"bound": "hbm", "kernel": "o2_hogwild_d128_kernel<ATOMIC=%s,NEG=5>" % ("true" if args.atomic else "false"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_pair": B_PAIR,
                 "pairs_per_launch": all_pairs / world / args.steps,
@@ -340,7 +344,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": (2 if world == 1 else 4) * args.steps, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -374,6 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--atomic", type=int, default=0, help="1: scatter with red.global.add.v4.f32")
+    ap.add_argument("--alias", type=int, default=0, help="1: draw negatives from the alias table (Hogwild option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tuning", type=int, nargs=3, default=None, metavar=("CENTRES", "MAXLEN", "BLOCKS"),
                     help="comemb_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm) for experiments")

@@ -79,6 +79,9 @@ def ensure_init():
         torch.cuda.init()
         torch.zeros(1, device="cuda")  # make sure the primary context is current
         check(load().comemb_init())
+        tune = os.environ.get("COMEMB_TUNING")  # "centres_per_unit,max_walk_len,blocks_per_sm" (experiments)
+        if tune:
+            check(load().comemb_set_tuning(*[int(v) for v in tune.split(",")]))
         _inited_devices.add(dev)
     return 0
 
