@@ -201,11 +201,12 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, atomic=True):
     return {"workload": "BASELINE configs[1]: synthetic SBM %dK nodes / ~2M edges / %d blocks, d=%d, walk len %d, "
                         "window %d, %d negatives; one step = one walk per node (%d walks) per GPU" % (
                             CFG["n"] // 1000, CFG["blocks"], CFG["d"], CFG["L"], CFG["W"], CFG["neg"], CFG["n"]),
             "table_size": CFG["table_size"], "lr": CFG["lr"], "mode": "hogwild",
+            "scatter": "red.global.add.v4.f32" if atomic else "plain 128-bit stores",
             "l2": "256 MiB flush write between timed steps; tables 2x51 MB",
             "parallelism": "replicated tables, walk stream sharded per GPU, NCCL all-reduce average every step"
             if n_gpus > 1 else "single GPU"}
@@ -343,7 +344,7 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, bool(args.atomic)),
             "clocks": clocks, "e2e": e2e, "gpu_launches": (2 if world == 1 else 4) * args.steps, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -377,7 +378,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--atomic", type=int, default=0, help="1: scatter with red.global.add.v4.f32")
+    ap.add_argument("--atomic", type=int, default=1,
+                    help="1 (default): scatter with red.global.add.v4.f32 (no lost updates); 0: plain stores")
     ap.add_argument("--alias", type=int, default=0, help="1: draw negatives from the alias table (Hogwild option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tuning", type=int, nargs=3, default=None, metavar=("CENTRES", "MAXLEN", "BLOCKS"),

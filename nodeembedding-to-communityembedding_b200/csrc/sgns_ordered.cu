@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(32)
     const int lane = threadIdx.x & 31;
     for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
     __syncwarp();
-    const float clipv = __fmul_rn(0.1f, lr);  // c:2556
+    const float clipv = __double2float_rn(__dmul_rn((double)lr, 0.1));  // c:2556 `_alpha = alpha * 0.1` (double product)
     const float nl2 = -lambda2;               // c:3132
     for (int64_t w = 0; w < n_walks; w++) {
         const uint32_t *path = walks + walk_off[w];

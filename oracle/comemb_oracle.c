@@ -464,7 +464,7 @@ int64_t oracle_train_sg(float *node, float *negemb, int size, const uint32_t *pa
             uint32_t word_index = path[i], word2_index = path[j];
             int64_t row1 = (int64_t)word2_index * size;
             /* (1) o3 */
-            float clipv = 0.1f * lr; /* c:2556 _alpha = alpha*0.1 */
+            float clipv = (float)((double)lr * 0.1); /* c:2556 `cdef REAL_t _alpha = alpha * 0.1` (double product) */
             float nl2 = -lambda2;    /* c:3132 */
             memset(work_o3, 0, (size_t)size * sizeof(float));
             if (nl2 != 0.0f) {

@@ -31,4 +31,4 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     g = os.path.join(ROOT, "tests", "golden")
-    return {name: np.load(os.path.join(g, "golden_%s.npz" % name)) for name in ("sgd", "walks", "karate")}
+    return {name: np.load(os.path.join(g, "golden_%s.npz" % name)) for name in ("sgd", "sg", "walks", "karate")}

@@ -43,6 +43,57 @@ O3_CASES = {
 }
 
 
+# legacy fused pass (stale train_sg): per pair o3 gradient + SGNS + combined write
+SG_CASES = {
+    "sg_d128_k3_ctx": dict(d=128, N=40, K=3, nw=4, L=12, W=2, neg=5, seed=500, lr=0.025, l1=1.0, l2=0.1, isnode=0),
+    "sg_d128_k3_nodeemb": dict(d=128, N=40, K=3, nw=3, L=12, W=2, neg=5, seed=501, lr=0.025, l1=1.0, l2=0.1, isnode=1),
+    "sg_d16_k4_w5": dict(d=16, N=40, K=4, nw=3, L=30, W=5, neg=3, seed=502, lr=0.05, l1=0.7, l2=0.2, isnode=0),
+    "sg_d2_k2_karate": dict(d=2, N=34, K=2, nw=5, L=20, W=3, neg=4, seed=503, lr=0.1, l1=1.0, l2=0.1, isnode=0),
+    "sg_d100_l2zero_w1": dict(d=100, N=40, K=3, nw=3, L=12, W=1, neg=5, seed=504, lr=0.025, l1=1.0, l2=0.0, isnode=0),
+    "sg_d64_onehot_none": dict(d=64, N=50, K=5, nw=4, L=16, W=3, neg=4, seed=505, lr=0.05, l1=1.0, l2=0.5, isnode=0,
+                               onehot=True, none_every=5),
+}
+
+
+def sg_inputs(c):
+    rs = np.random.RandomState(c["seed"])
+    d, N, K = c["d"], c["N"], c["K"]
+    node = (rs.uniform(-1, 1, (N, d)) * 0.5).astype(np.float32)
+    ctx = (rs.uniform(-1, 1, (N, d)) * 0.5).astype(np.float32)
+    table = make_table(rs, N)
+    mu = rs.uniform(-0.5, 0.5, (K, d)).astype(np.float32)
+    inv = (rs.normal(size=(K, d, d)) * 0.3).astype(np.float32)  # deliberately not symmetric (column-major read!)
+    if c.get("onehot"):
+        pi = np.zeros((N, K), np.float32)
+        pi[np.arange(N), rs.randint(0, K, size=N)] = 1.0
+    else:
+        p = rs.uniform(0, 1, (N, K)) ** 3
+        pi = (p / p.sum(1, keepdims=True)).astype(np.float32)
+    walks = []
+    for w in range(c["nw"]):
+        t = rs.randint(0, N, size=c["L"]).astype(np.uint32)
+        if c.get("none_every"):
+            t[::c["none_every"]] = TOKEN_NONE
+        walks.append(t)
+    return node, ctx, table, mu, inv, pi, walks
+
+
+def sg_draws(rs, walks, window):
+    """np.random consumption of the legacy train_sg per call: the LCG seed (2 draws), then one randint(window) per
+    non-None token when window > 1 (old-pyx:343, 356-364).  Returns (seeds uint64[nw], reduced windows flat int32)."""
+    seeds, rws = [], []
+    for w in walks:
+        r = rs.randint(0, 2 ** 24, size=2).astype(np.uint64)
+        seeds.append((r[0] << np.uint64(24)) + r[1])
+        rw = np.zeros(len(w), np.int32)
+        if window > 1:
+            for i, t in enumerate(w):
+                if int(t) != TOKEN_NONE:
+                    rw[i] = rs.randint(window)
+        rws.append(rw)
+    return np.asarray(seeds, np.uint64), (np.concatenate(rws) if rws else np.zeros(0, np.int32))
+
+
 def make_table(rs, N, size=1000):
     """A small negative table with the reference's quirk: values in 1..N-1 (node ids used as rows), monotone."""
     return np.sort(rs.randint(1, N, size=size)).astype(np.uint32)

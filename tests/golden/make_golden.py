@@ -10,7 +10,8 @@
   * karate: config 1 -- Model + Node2Vec.train + Context2Vec.train + Community2Vec.train at d=128 through the
     reference's own learner classes (workers=1), GMM parameters recorded as inputs.
 
-Outputs (committed): tests/golden/golden_sgd.npz, golden_walks.npz, golden_karate.npz, golden_meta.json.
+Outputs (committed): tests/golden/golden_sgd.npz, golden_sg.npz (legacy fused train_sg, from the stale Cython
+kernel rebuilt by oracle/build_ref_legacy.py), golden_walks.npz, golden_karate.npz, golden_meta.json.
 Run:  python tests/golden/make_golden.py        (needs /root/reference; never runs on the GPU box)
 """
 import hashlib
@@ -55,6 +56,28 @@ def gen_sgd(ref, out):
         for e in edges:
             tot += ref.train_o1(node, to_path(e), c["lr"], c["neg"], table, py_size=c["d"], py_work=work)
         out[name + "/node"] = node
+        out[name + "/ret"] = np.int64(tot)
+
+
+def gen_sg(out):
+    """Legacy fused train_sg: the stale Cython kernel rebuilt by oracle/build_ref_legacy.py."""
+    from oracle import build_ref_legacy
+    build_ref_legacy.main()
+    leg = O.load_ref("legacy")
+    assert leg.FAST_VERSION == 0
+    for name, c in cases.SG_CASES.items():
+        node, ctx, table, mu, inv, pi, walks = cases.sg_inputs(c)
+        d = c["d"]
+        negemb = node if c["isnode"] else ctx
+        np.random.seed(c["seed"] + 7)
+        w = [np.zeros(d, np.float32) for _ in range(3)] + [np.zeros(d * d, np.float32)]
+        tot = 0
+        for path in walks:
+            tot += leg.train_sg(node, negemb, to_path(path), c["lr"], c["neg"], c["W"], table, mu, inv, pi, c["K"], inv,
+                                py_lambda1=c["l1"], py_lambda2=c["l2"], py_size=d, py_work=w[0], py_work_o3=w[1],
+                                py_work1_o3=w[2], py_work2_o3=w[3], py_is_node_embedding=c["isnode"])
+        out[name + "/node"] = node
+        out[name + "/ctx"] = ctx
         out[name + "/ret"] = np.int64(tot)
 
 
@@ -211,6 +234,10 @@ def main():
                             python=sys.version.split()[0])
     meta["blas"] = [dict(prefix=i.get("prefix"), version=i.get("version"), architecture=i.get("architecture"))
                     for i in threadpool_info()]
+    sg_out = {}
+    gen_sg(sg_out)
+    np.savez_compressed(os.path.join(HERE, "golden_sg.npz"), **sg_out)
+    ref = O.load_ref("tuned", with_python_sources=True)
     for fname, gen in (("golden_sgd.npz", lambda o: (gen_sgd(ref, o), gen_o3(o), gen_table(o))),):
         out = {}
         gen(out)
@@ -221,7 +248,7 @@ def main():
     out = {}
     gen_karate(out, G, gu)
     np.savez_compressed(os.path.join(HERE, "golden_karate.npz"), **out)
-    for f in ("golden_sgd.npz", "golden_walks.npz", "golden_karate.npz"):
+    for f in ("golden_sgd.npz", "golden_sg.npz", "golden_walks.npz", "golden_karate.npz"):
         meta[f] = hashlib.sha256(open(os.path.join(HERE, f), "rb").read()).hexdigest()
     json.dump(meta, open(os.path.join(HERE, "golden_meta.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(meta, indent=1))

@@ -124,3 +124,27 @@ def test_karate_pipeline_config1(golden):
         assert np.abs(cur - want).max() <= 1e-5 * np.abs(want).max(), (it, np.abs(cur - want).max())
         prev = want.copy()
     assert np.array_equal(prev, g["final_node"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.SG_CASES))
+def test_legacy_fused_train_sg(golden, name):
+    """A7: the oracle's restatement of the stale fused train_sg vs the stale Cython kernel itself (rebuilt by
+    oracle/build_ref_legacy.py).  The o3 term goes through BLAS sgemm in the reference (summation order
+    unspecified): 1e-6 of the table scale; bit-exact when lambda2 == 0."""
+    c = cases.SG_CASES[name]
+    node, ctx, table, mu, inv, pi, walks = cases.sg_inputs(c)
+    seeds, rws = cases.sg_draws(np.random.RandomState(c["seed"] + 7), walks, c["W"])
+    negemb = node if c["isnode"] else ctx
+    tot, pos = 0, 0
+    for w, s in zip(walks, seeds):
+        rw = np.ascontiguousarray(rws[pos:pos + len(w)]) if c["W"] > 1 else None
+        pos += len(w)
+        tot += O.train_sg(node, negemb, np.ascontiguousarray(w), rw, c["lr"], c["neg"], c["W"], table, mu, inv, pi,
+                          c["l1"], c["l2"], c["isnode"], int(s))
+    g = golden["sg"]
+    assert tot == int(g[name + "/ret"])
+    tol = 0.0 if c["l2"] == 0.0 else 1e-6
+    assert np.abs(node - g[name + "/node"]).max() <= tol * np.abs(g[name + "/node"]).max()
+    assert np.abs(ctx - g[name + "/ctx"]).max() <= tol * np.abs(g[name + "/ctx"]).max()
+    before = cases.sg_inputs(c)[0]
+    assert np.abs(g[name + "/node"] - before).max() > 1e-3
