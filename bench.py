@@ -32,8 +32,11 @@ METRIC = "sgns_pair_updates_per_sec"
 UNIT = "pair-updates/s"
 B_PAIR = 4 * 128 * (2 + 2 * (5 + 1))  # algorithmic bytes per pair update at d=128, neg=5: 7168
 
-CFG = dict(n=100000, blocks=50, avg_degree=40, d=128, L=80, W=10, neg=5, lr=0.025, table_size=5000000,
-           graph_seed=12345)
+CFG = dict(name="sbm", n=100000, blocks=50, avg_degree=40, d=128, L=80, W=10, neg=5, lr=0.025, table_size=5000000,
+           graph_seed=12345, walks_per_step=100000)
+# BASELINE configs[3] shape (tables 2 x 563 MB: far beyond L2, the HBM-bound regime); not the default bench line
+CFG_YOUTUBE = dict(name="youtube", n=1100000, n_edges=3000000, d=128, L=80, W=10, neg=5, lr=0.025,
+                   table_size=100000000, graph_seed=12345, walks_per_step=200000)
 
 
 def pairs_of_len(length, W):
@@ -154,6 +157,8 @@ def host_walks(G, n_walks, L, seed):
 
 def build_workload():
     from comemb_b200.utils import graph_utils as gu
+    if CFG["name"] == "youtube":
+        return gu.powerlaw_graph(CFG["n"], CFG["n_edges"], seed=CFG["graph_seed"]), None
     G, block = gu.sbm_graph(CFG["n"], CFG["blocks"], CFG["avg_degree"], seed=CFG["graph_seed"])
     return G, block
 
@@ -202,12 +207,18 @@ def run_reference(args):
 
 
 def workload_config(n_gpus, atomic=True):
-    return {"workload": "BASELINE configs[1]: synthetic SBM %dK nodes / ~2M edges / %d blocks, d=%d, walk len %d, "
-                        "window %d, %d negatives; one step = one walk per node (%d walks) per GPU" % (
-                            CFG["n"] // 1000, CFG["blocks"], CFG["d"], CFG["L"], CFG["W"], CFG["neg"], CFG["n"]),
+    if CFG["name"] == "youtube":
+        wl = ("BASELINE configs[3] shape: synthetic power-law graph %.1fM nodes / %.0fM edges, d=%d, walk len %d, window "
+              "%d, %d negatives; one step = %d walks per GPU" % (CFG["n"] / 1e6, CFG["n_edges"] / 1e6, CFG["d"],
+                                                                 CFG["L"], CFG["W"], CFG["neg"], CFG["walks_per_step"]))
+    else:
+        wl = ("BASELINE configs[1]: synthetic SBM %dK nodes / ~2M edges / %d blocks, d=%d, walk len %d, "
+              "window %d, %d negatives; one step = one walk per node (%d walks) per GPU" % (
+                  CFG["n"] // 1000, CFG["blocks"], CFG["d"], CFG["L"], CFG["W"], CFG["neg"], CFG["n"]))
+    return {"workload": wl,
             "table_size": CFG["table_size"], "lr": CFG["lr"], "mode": "hogwild",
             "scatter": "red.global.add.v4.f32" if atomic else "plain 128-bit stores",
-            "l2": "256 MiB flush write between timed steps; tables 2x51 MB",
+            "l2": "256 MiB flush write between timed steps; tables 2x%d MB" % (CFG["n"] * CFG["d"] * 4 // 1000000),
             "parallelism": "replicated tables, walk stream sharded per GPU, NCCL all-reduce average every step"
             if n_gpus > 1 else "single GPU"}
 
@@ -241,9 +252,10 @@ def run_ours(args):
     node_h, ctx_h = init_tables_host(n, d)
     node, ctx = torch.from_numpy(node_h).cuda(), torch.from_numpy(ctx_h).cuda()
     rowptr, col = G.device()
-    walks = torch.empty((n, L), dtype=torch.int32, device="cuda")
-    lens = torch.empty(n, dtype=torch.int32, device="cuda")
-    off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+    nws = CFG["walks_per_step"]
+    walks = torch.empty((nws, L), dtype=torch.int32, device="cuda")
+    lens = torch.empty(nws, dtype=torch.int32, device="cuda")
+    off = torch.arange(nws + 1, dtype=torch.int64, device="cuda") * L
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
     lib = _lib.load()
@@ -255,9 +267,9 @@ def run_ours(args):
 
     def step(s, ev=None):
         """one pass: walker kernel (this rank's walk stream) + Hogwild o2 kernel [+ replica averaging]"""
-        g_first = (s * world + rank) * n  # distinct walk ids per (step, rank) -> distinct random streams
+        g_first = (s * world + rank) * nws  # distinct walk ids per (step, rank) -> distinct random streams
         _lib.check(lib.comemb_walks_csr(rowptr.data_ptr(), col.data_ptr(), n, 1 << 20, L, 0.0, 777, K.MODE_HOGWILD,
-                                        g_first, n, walks.data_ptr(), lens.data_ptr(), stream.cuda_stream))
+                                        g_first, nws, walks.data_ptr(), lens.data_ptr(), stream.cuda_stream))
         if ev:
             ev[0].record(stream)
         K.o2_batch(node, ctx, walks.reshape(-1), off, None, lr, neg, W, table, mode=K.MODE_HOGWILD, flags=flags,
@@ -303,12 +315,12 @@ def run_ours(args):
 
     # ---- end-to-end through host buffers (pinned host memory -> device -> host, every step) ----------------------------
     e2e = None
-    runner = K.HostO2Runner(n, d, n * L, n, table)
+    runner = K.HostO2Runner(n, d, nws * L, nws, table)
     wh = walks.cpu().numpy().view(np.uint32).reshape(-1).copy()
-    offh = (np.arange(n + 1) * L).astype(np.int64)
+    offh = (np.arange(nws + 1) * L).astype(np.int64)
     nh, ch = node.cpu().numpy(), ctx.cpu().numpy()
     e2e_pairs = int(pairs_lut[lens.long()].sum().item())
-    seeds_h = K.draw_seeds(n, np.random.RandomState(5))
+    seeds_h = K.draw_seeds(nws, np.random.RandomState(5))
     ms = []
     for s in range(1 + max(1, args.steps // 2)):
         torch.cuda.synchronize()
@@ -328,7 +340,7 @@ def run_ours(args):
     o2_pairs_per_s = (all_pairs / world) / (o2_total_ms * 1e-3)  # per GPU, the dominant kernel alone
     achieved = o2_pairs_per_s * B_PAIR / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "o2_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "o2_traffic.json" if CFG["name"] == "sbm" else "o2_traffic_%s.json" % CFG["name"])
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
@@ -339,8 +351,9 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_pair": B_PAIR,
                 "pairs_per_launch": all_pairs / world / args.steps,
                 "kernel_ms_per_launch": o2_total_ms / args.steps,
-                "note": "tables (2 x 51 MB) fit the 126 MB L2: algorithmic bytes are served mostly by L2, so frac can "
-                        "exceed what DRAM alone would allow"}
+                "note": ("tables (2 x 51 MB) fit the 126 MB L2: algorithmic bytes are served mostly by L2, so frac can "
+                         "exceed what DRAM alone would allow") if CFG["name"] == "sbm" else
+                        "tables (2 x 563 MB) exceed L2: the gather/scatter is served by HBM"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -352,7 +365,7 @@ def run_ours(args):
             from oracle import oracle as O
             threads = os.cpu_count() or 1
             nw = max(threads, int(threads * 3e5 * 12 / pairs_of_len(L, W)))  # ~12 s of CPU work
-            nw = min(nw, n)
+            nw = min(nw, nws)
             wnp = walks.cpu().numpy().view(np.uint32)
             ln = lens.cpu().numpy()
             ws = [wnp[i, :ln[i]].copy() for i in range(nw)]
@@ -372,6 +385,70 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_secondary(args):
+    """Secondary kernels of the path on the same SBM workload (not the judged line): o1 directed updates/s and o3
+    (HEAD full-batch community step) node updates/s, device-timed with CUDA events."""
+    import torch
+    import comemb_b200.utils.training_sdg_inner as K
+    from comemb_b200 import _lib
+    torch.cuda.set_device(0)
+    K.init()
+    G, block = build_workload()
+    n, d, neg = CFG["n"], CFG["d"], CFG["neg"]
+    node_h, _ = init_tables_host(n, d)
+    node = torch.from_numpy(node_h * 0.05).cuda()
+    peak, _ = measured_peak()
+    out = {"config": workload_config(1), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "data": "synthetic"}
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        ts = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    if args.kernel == "o1":
+        deg = np.ascontiguousarray(np.diff(G.rowptr), np.float64)
+        table = torch.empty(CFG["table_size"], dtype=torch.int32, device="cuda")
+        _lib.check(_lib.load().comemb_make_table(deg.ctypes.data, deg.size, 0.75, table.data_ptr(), table.numel(), None))
+        src = np.repeat(np.arange(n, dtype=np.int64), np.diff(G.rowptr))
+        keep = src < G.col
+        edges = torch.from_numpy(np.stack([src[keep], G.col[keep].astype(np.int64)], 1).astype(np.int32)).cuda()
+        E = edges.shape[0]
+        from comemb_b200.ADSCModel.node_embeddings import _coprime_stride
+        stride = _coprime_stride(E)
+        ms = timed(lambda: K.o1_batch(node, edges, None, 0.025, neg, table, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC,
+                                      base_seed=3, edge_stride=stride))
+        v = 2 * E / (ms * 1e-3)
+        out.update({"metric": "o1_directed_updates_per_sec", "value": v, "unit": "directed-updates/s", "ms_per_step": ms,
+                    "edges": E, "roofline": {"bound": "hbm", "achieved": v * 4096 / 1e9, "peak": peak, "unit": "GB/s",
+                                             "frac": v * 4096 / 1e9 / peak, "algorithmic_bytes_per_update": 4096}})
+    else:
+        Kc = CFG.get("blocks", 50)
+        rs = np.random.RandomState(0)
+        mu = torch.from_numpy(rs.uniform(-0.5, 0.5, (Kc, d)).astype(np.float32)).cuda()
+        a = rs.normal(size=(Kc, d, d)).astype(np.float32) * 0.05
+        inv = torch.from_numpy(a + np.eye(d, dtype=np.float32)).cuda()
+        pi_h = np.zeros((n, Kc), np.float32)
+        pi_h[np.arange(n), block % Kc] = 1.0  # sklearn's predict_proba is one-hot in fp32 on separated data
+        pi = torch.from_numpy(pi_h).cuda()
+        inv_t = K.transpose_blocks(inv)
+        ms = timed(lambda: K.o3_batch(node, None, mu, inv_t, pi, 0.1, 0.025, iters=1))
+        v = n / (ms * 1e-3)
+        out.update({"metric": "o3_node_updates_per_sec", "value": v, "unit": "node-updates/s", "ms_per_step": ms,
+                    "K": Kc, "pi": "one-hot", "flop_per_node": 2 * d * d,
+                    "roofline": {"bound": "l2/fp64-fma", "achieved_gflops": v * 2 * d * d / 1e9,
+                                 "l2_read_gbs": v * d * d * 4 / 1e9}})
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -380,13 +457,22 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--atomic", type=int, default=1,
                     help="1 (default): scatter with red.global.add.v4.f32 (no lost updates); 0: plain stores")
+    ap.add_argument("--workload", default="sbm", choices=["sbm", "youtube"],
+                    help="sbm = BASELINE configs[1] (the judged line); youtube = configs[3] shape (HBM-bound regime)")
+    ap.add_argument("--kernel", default="o2", choices=["o2", "o1", "o3"],
+                    help="o2 = the judged metric; o1 / o3 = secondary kernels of the path (separate JSON line)")
     ap.add_argument("--alias", type=int, default=0, help="1: draw negatives from the alias table (Hogwild option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tuning", type=int, nargs=3, default=None, metavar=("CENTRES", "MAXLEN", "BLOCKS"),
                     help="comemb_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm) for experiments")
     args = ap.parse_args()
+    if args.workload == "youtube":
+        CFG.clear()
+        CFG.update(CFG_YOUTUBE)
     if args.impl == "reference":
         run_reference(args)
+    elif args.kernel != "o2":
+        run_secondary(args)
     else:
         run_ours(args)
 

@@ -121,6 +121,23 @@ def sbm_graph(n, n_blocks, avg_degree, p_in=0.8, seed=12345):
     return G, block
 
 
+def powerlaw_graph(n, n_edges, exponent=2.1, seed=12345, max_degree=None):
+    """Chung-Lu style synthetic graph with a power-law expected-degree sequence (BASELINE.json configs[2..3] shapes:
+    BlogCatalog / Youtube).  Every node gets at least one edge (a ring edge) so that no walk dead-ends."""
+    rs = np.random.RandomState(seed)
+    w = (np.arange(1, n + 1, dtype=np.float64)) ** (-1.0 / (exponent - 1.0))
+    if max_degree:
+        w = np.minimum(w, w[0] * max_degree / (2.0 * n_edges * w[0] / w.sum()))
+    p = w / w.sum()
+    cdf = np.cumsum(p)
+    src = np.searchsorted(cdf, rs.random_sample(n_edges)).clip(0, n - 1)
+    dst = np.searchsorted(cdf, rs.random_sample(n_edges)).clip(0, n - 1)
+    perm = rs.permutation(n)  # hubs scattered over the id space
+    ring = np.stack([np.arange(n), (np.arange(n) + 1) % n], 1)
+    e = np.concatenate([np.stack([perm[src], perm[dst]], 1), ring]) + 1
+    return from_edge_array_fast(e, n)
+
+
 def from_csr(ids, rowptr, col):
     return Graph(ids, rowptr, col)
 
