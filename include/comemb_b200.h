@@ -50,6 +50,10 @@ int comemb_abi_version(void);
 /* Hogwild work decomposition: centres_per_unit = 0 -> one warp per walk (the reference's per-thread granularity);
  * > 0 -> one warp per chunk of that many centres (needs max_walk_len); blocks_per_sm = 0 -> occupancy query. */
 int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm);
+/* HOGWILD concurrency cap: at most `max_warps` walks/edges are processed at the same time (0 = fill the GPU).  The
+ * reference's `workers` count plays this role; the learners set max(workers, n_rows/28) so that the expected number
+ * of concurrent updates hitting one row stays below ~1/4 on small graphs (karate: 34 rows). */
+int comemb_set_max_warps(int64_t max_warps);
 const char *comemb_error_string(int code);
 
 /* ---- o2: replaces train_o2 (pyx:454-509) applied to a batch of paths, i.e. the worker loop of
@@ -103,6 +107,16 @@ int comemb_sg_fused(float *d_node, float *d_negemb, int64_t n_rows, int size, co
                     const float *d_mu, const float *d_inv_cov, const float *d_pi, int K, int window, int negative,
                     float lr, float lambda1, float lambda2, int is_node_embedding, int mode, uint32_t flags,
                     void *stream);
+
+/* ---- Python-twin semantics of the fused pass: replaces the fallback train_sg / gradient_update / community_sdg of
+ * utils/embedding.py:15-98 (exact sigmoid, negatives redrawn until != both nodes, vectorised update where duplicate
+ * targets keep the last write, float64 intermediates, inv_cov NOT transposed).  The host enumerates the window pairs and
+ * draws the targets with the twin's own np.random loop; d_pair_row[p] = row of node2, d_targets[p*(negative+1)+k] =
+ * target rows (positive first).  One warp, sequential.  negative <= 7. */
+int comemb_sg_twin(float *d_node, float *d_ctx, int64_t n_rows, int size, const uint32_t *d_pair_row,
+                   const uint32_t *d_targets, int64_t n_pairs, int negative, double alpha, double lambda1,
+                   double lambda2, const float *d_mu, const float *d_inv_cov, const float *d_pi, int K,
+                   int is_node_embedding, void *stream);
 
 /* ---- walks: replaces __random_walk__ / build_deepwalk_corpus_iter (utils/graph_utils.py:20-46, 191-197) -----------------
  * CSR over row numbers: d_rowptr int64 [n+1], d_col uint32.  Output d_walks uint32 [num_paths*n, path_length] padded

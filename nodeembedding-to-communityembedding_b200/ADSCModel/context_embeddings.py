@@ -16,7 +16,7 @@ from ..utils.embedding import paths_to_rows
 
 
 class Context2Vec(object):
-    def __init__(self, lr=0.1, window_size=5, workers=1, negative=5, mode=None, atomic=False, use_alias=False):
+    def __init__(self, lr=0.1, window_size=5, workers=1, negative=5, mode=None, atomic=True, use_alias=False):
         self.lr = float(lr)
         self.workers = workers
         self.negative = negative
@@ -65,7 +65,9 @@ class Context2Vec(object):
         with torch.cuda.device(dev):
             tokens = K.o2_batch(model.node_embedding, model.context_embedding, walks, off, seeds, self.lr, self.negative,
                                 self.window_size, model.table, alpha=alpha, mode=mode, flags=flags, alias=alias,
-                                count_tokens=True)
+                                count_tokens=True,
+                                max_warps=K.hogwild_concurrency(model.vocab_size, self.workers)
+                                if mode == K.MODE_HOGWILD else 0)
         elapsed = time.time() - start
         log.info("training on %i nodes took %.1fs, %.0f nodes/s" % (node_count + tokens, elapsed,
                                                                      (node_count + tokens) / elapsed if elapsed else 0.0))

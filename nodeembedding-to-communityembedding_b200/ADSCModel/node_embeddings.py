@@ -68,7 +68,8 @@ class Node2Vec(object):
             stride = _coprime_stride(n_edges)
         with torch.cuda.device(dev):
             K.o1_batch(model.node_embedding, e, seeds, self.lr, self.negative, model.table, mode=mode, flags=flags,
-                       edge_stride=stride)
+                       edge_stride=stride,
+                       max_warps=K.hogwild_concurrency(model.vocab_size, self.workers) if mode == K.MODE_HOGWILD else 0)
             torch.cuda.current_stream().synchronize()
         elapsed = time.time() - start
         log.info("training on %i words took %.1fs, %.0f words/s" % (2 * n_edges, elapsed,

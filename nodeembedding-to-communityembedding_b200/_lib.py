@@ -22,6 +22,7 @@ SIGNATURES = {
     "comemb_get_lut": (_i32, [_vp]),
     "comemb_abi_version": (_i32, []),
     "comemb_set_tuning": (_i32, [_i32, _i32, _i32]),
+    "comemb_set_max_warps": (_i32, [_i64]),
     "comemb_error_string": (_c.c_char_p, [_i32]),
     "comemb_o2_walks": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _u64, _vp, _u64, _vp, _u32, _i32, _i32,
                                _f32, _f32, _i32, _u32, _vp, _vp]),
@@ -31,6 +32,8 @@ SIGNATURES = {
     "comemb_transpose_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "comemb_sg_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32,
                                _i32, _i32, _f32, _f32, _f32, _i32, _i32, _u32, _vp]),
+    "comemb_sg_twin": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _f64, _f64, _f64, _vp, _vp, _vp, _i32, _i32,
+                              _vp]),
     "comemb_walks_csr": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _u64, _i32, _i64, _i64, _vp, _vp, _vp]),
     "comemb_make_table": (_i32, [_vp, _i64, _f64, _vp, _i64, _vp]),
     "comemb_build_alias": (_i32, [_vp, _i64, _i64, _vp, _vp]),

@@ -22,6 +22,9 @@ int launch_sg_fused_hogwild(float *, float *, int, const uint32_t *, const int64
                             const uint64_t *, uint64_t, const uint32_t *, uint64_t, const float *, const float *,
                             const float *, int, int, int, float, float, float, int, bool, cudaStream_t);
 void hogwild_set_tuning(int, int, int);
+void hogwild_set_max_warps(int64_t);
+int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
+                   const float *, const float *, const float *, int, int, cudaStream_t);
 int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const float *, const float *, const float *, int,
                     double, float, int, cudaStream_t);
 int launch_transpose_blocks(const float *, float *, int, int, cudaStream_t);
@@ -97,6 +100,12 @@ int comemb_get_lut(float *h_lut1000) {
 int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm) {
     if (centres_per_unit < 0 || max_walk_len < 0 || blocks_per_sm < 0) return COMEMB_E_ARG;
     hogwild_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm);
+    return 0;
+}
+
+int comemb_set_max_warps(int64_t max_warps) {
+    if (max_warps < 0) return COMEMB_E_ARG;
+    hogwild_set_max_warps(max_warps);
     return 0;
 }
 
@@ -181,6 +190,17 @@ int comemb_sg_fused(float *d_node, float *d_negemb, int64_t n_rows, int size, co
                                        base_seed, d_table, table_len, d_mu, d_inv_cov, d_pi, K, window, negative, lr,
                                        lambda1, lambda2, is_node_embedding, (flags & COMEMB_F_ATOMIC) != 0, st);
     return COMEMB_E_ARG;
+}
+
+int comemb_sg_twin(float *d_node, float *d_ctx, int64_t n_rows, int size, const uint32_t *d_pair_row,
+                   const uint32_t *d_targets, int64_t n_pairs, int negative, double alpha, double lambda1,
+                   double lambda2, const float *d_mu, const float *d_inv_cov, const float *d_pi, int K,
+                   int is_node_embedding, void *stream) {
+    if (!d_node || !d_ctx || n_rows <= 0 || size <= 0 || n_pairs < 0 || negative < 0) return COMEMB_E_ARG;
+    if (n_pairs > 0 && (!d_pair_row || !d_targets)) return COMEMB_E_ARG;
+    if (lambda2 > 0.0 && (K <= 0 || !d_mu || !d_inv_cov || !d_pi)) return COMEMB_E_ARG;
+    return launch_sg_twin(d_node, d_ctx, size, d_pair_row, d_targets, n_pairs, negative, alpha, lambda1, lambda2, d_mu,
+                          d_inv_cov, d_pi, K, is_node_embedding, (cudaStream_t)stream);
 }
 
 int comemb_walks_csr(const int64_t *d_rowptr, const uint32_t *d_col, int64_t n, int num_paths, int path_length,

@@ -14,6 +14,8 @@
 // fused pass is bound by the o3 term (FP64-FMA / L2), not by HBM.
 #include "comemb_common.cuh"
 
+int64_t hogwild_get_max_warps();
+
 namespace {
 
 constexpr int WARPS = 8;
@@ -188,7 +190,10 @@ int launch_t(const SgParams &P, bool atomic, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = (P.n_walks + WARPS - 1) / WARPS;
-    const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
+    int64_t cap = (int64_t)sms * 4;
+    if (hogwild_get_max_warps() > 0 && (hogwild_get_max_warps() + WARPS - 1) / WARPS < cap)
+        cap = (hogwild_get_max_warps() + WARPS - 1) / WARPS;
+    const int grid = (int)(want < cap ? want : cap);
     const size_t smem = (EXP_TABLE_SIZE + (size_t)WARPS * P.d) * sizeof(float);
     if (atomic)
         sg_fused_hogwild_kernel<NCH, true><<<grid, WARPS * 32, smem, st>>>(P);

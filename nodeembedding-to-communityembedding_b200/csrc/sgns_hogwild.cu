@@ -22,6 +22,7 @@ struct Tuning {
     int centres_per_unit = 0;  // 0 = a whole walk per warp
     int max_walk_len = 0;      // needed when centres_per_unit > 0
     int blocks_per_sm = 0;     // 0 = occupancy query
+    int64_t max_warps = 0;     // 0 = fill the GPU; else cap on concurrently running walks/edges (Hogwild staleness)
     int variant = 0;           // d=128 o2 kernel: 3 -> 80-register build (3 CTAs/SM), else 64-register build (4 CTAs/SM)
 };
 Tuning g_tuning;
@@ -881,6 +882,10 @@ int grid_for(K kernel, int64_t n_units, size_t dyn_smem = 0) {
     if (per_sm < 1) per_sm = 1;
     int64_t want = (n_units + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int64_t cap = (int64_t)sms * per_sm;  // a multiple of the SM count: every SM holds its full complement of warps
+    if (g_tuning.max_warps > 0) {
+        const int64_t lim = (g_tuning.max_warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        if (lim < cap) cap = lim;
+    }
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -941,6 +946,9 @@ int launch_o1_t(const O1Params &P, bool atomic, cudaStream_t st) {
 }
 
 }  // namespace
+
+void hogwild_set_max_warps(int64_t max_warps) { g_tuning.max_warps = max_warps; }
+int64_t hogwild_get_max_warps() { return g_tuning.max_warps; }
 
 void hogwild_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm) {
     g_tuning.centres_per_unit = centres_per_unit;

@@ -280,6 +280,80 @@ __global__ void __launch_bounds__(32)
     }
 }
 
+
+// ---- Python-twin semantics (utils/embedding.py:15-98): explicit target lists, exact sigmoid, vectorised update ------------
+// One pair = (node2 row, neg+1 target rows [positive first]) prepared by the host, which also draws the negatives
+// with the twin's own rejection loop on np.random (embedding.py:48-52).  Per pair, as the numpy code does it:
+//   fb_k  = expit(float32 dot(x, c_k))            all k from the OLD context rows            (:78-83)
+//   gb_k  = (label_k - fb_k) * alpha              float64
+//   work  = sum_k gb_k * c_k                      float64                                    (:58)
+//   o3    = -clip(sum_c (pi*inv_cov[c]) @ (x - mu_c) * lambda2, +-0.1*alpha)   float32, inv_cov NOT transposed (:86-98)
+//   ctx[t_k] = float32(c_k + gb_k * x)            computed from the gathered copy: duplicates -> last one wins (:67)
+//   x     = float32(x + (lambda1*work + o3))                                                   (:70)
+// smem: xs[size] | newx[size] | cold[(neg+1)*size]
+__global__ void __launch_bounds__(32)
+    sg_twin_kernel(float *node, float *ctxemb, int size, const uint32_t *pair_row, const uint32_t *targets,
+                   int64_t n_pairs, int negative, double alpha, double lambda1, double lambda2, const float *mu,
+                   const float *inv_cov, const float *pi, int K, int is_node_embedding) {
+    extern __shared__ float smem[];
+    float *xs = smem;
+    float *newx = smem + size;
+    float *cold = smem + 2 * size;
+    const int lane = threadIdx.x & 31;
+    const int T = negative + 1;  // <= 8 (checked by the launcher)
+    for (int64_t p = 0; p < n_pairs; p++) {
+        const uint32_t n2 = pair_row[p];
+        const uint32_t *t = targets + p * T;
+        float *x = node + (int64_t)n2 * size;
+        __syncwarp();
+        for (int e = lane; e < size; e += 32) xs[e] = x[e];
+        for (int k = 0; k < T; k++)
+            for (int e = lane; e < size; e += 32) cold[k * size + e] = ctxemb[(int64_t)t[k] * size + e];
+        __syncwarp();
+        double gb[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            gb[k] = 0.0;
+            if (k < T) {
+                double acc = 0.0;
+                for (int e = lane; e < size; e += 32) acc += (double)xs[e] * (double)cold[k * size + e];
+                for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+                const float f = (float)acc;                            // np.dot of float32 operands -> float32
+                const float fb = 1.0f / (1.0f + expf(-f));            // scipy.special.expit on float32
+                gb[k] = ((k == 0 ? 1.0 : 0.0) - (double)fb) * alpha;  // float64
+            }
+        }
+        for (int e = lane; e < size; e += 32) {
+            double work = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (k < T) work += gb[k] * (double)cold[k * size + e];
+            float o3 = 0.f;
+            if (lambda2 > 0.0) {
+                float grad = 0.f;
+                for (int c = 0; c < K; c++) {
+                    const float pw = pi[(int64_t)n2 * K + c];
+                    const float *S = inv_cov + (int64_t)c * size * size + (int64_t)e * size;  // row e: NOT transposed
+                    double sdot = 0.0;
+                    for (int b = 0; b < size; b++)
+                        sdot += (double)__fmul_rn(pw, S[b]) * (double)(xs[b] - mu[(int64_t)c * size + b]);
+                    grad = grad + __fmul_rn((float)sdot, (float)lambda2);
+                }
+                const float lim = (float)(0.1 * alpha);
+                o3 = -fminf(fmaxf(grad, -lim), lim);
+            }
+            newx[e] = (float)((double)xs[e] + (lambda1 * work + (double)o3));
+            if (!is_node_embedding) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (k < T) ctxemb[(int64_t)t[k] * size + e] = (float)((double)cold[k * size + e] + gb[k] * (double)xs[e]);
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < size; e += 32) x[e] = newx[e];
+    }
+}
+
 }  // namespace
 
 // ---- launchers (called from capi.cu) -------------------------------------------------------------------------------------
@@ -319,5 +393,19 @@ int launch_sg_fused_ordered(float *node, float *negemb, int size, const uint32_t
     sg_fused_ordered_kernel<<<1, 32, smem, st>>>(node, negemb, size, walks, walk_off, n_walks, reduced_windows, seeds,
                                                  base_seed, S, mu, inv_cov, pi, K, window, negative, lr, lambda1,
                                                  lambda2, is_node_embedding, quirk, comemb_lut_device());
+    return (int)cudaGetLastError();
+}
+
+int launch_sg_twin(float *node, float *ctxemb, int size, const uint32_t *pair_row, const uint32_t *targets,
+                   int64_t n_pairs, int negative, double alpha, double lambda1, double lambda2, const float *mu,
+                   const float *inv_cov, const float *pi, int K, int is_node_embedding, cudaStream_t st) {
+    if (negative + 1 > 8) return COMEMB_E_UNSUPPORTED;
+    if (n_pairs == 0) return 0;
+    size_t smem = (size_t)(negative + 3) * size * sizeof(float);
+    if (smem > 200 * 1024) return COMEMB_E_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(sg_twin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sg_twin_kernel<<<1, 32, smem, st>>>(node, ctxemb, size, pair_row, targets, n_pairs, negative, alpha, lambda1, lambda2,
+                                        mu, inv_cov, pi, K, is_node_embedding);
     return (int)cudaGetLastError();
 }

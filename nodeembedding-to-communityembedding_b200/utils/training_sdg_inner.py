@@ -138,8 +138,28 @@ def _indices(py_items):
 
 
 # ---- batch entry points -------------------------------------------------------------------------------------------------
+def hogwild_concurrency(n_rows, workers=1):
+    """Cap on concurrently processed walks/edges in HOGWILD mode: the reference's `workers`, or as many as keep the
+    expected number of in-flight updates per table row below ~1/4 (7 rows per pair -> n_rows/28), whichever is larger.
+    100K rows -> 3571 (a full B200 holds 3552 warps of the o2 kernel); karate -> `workers`."""
+    return int(max(int(workers), int(n_rows) // 28, 1))
+
+
+class _max_warps(object):
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        if self.n:
+            _lib.check(_lib.load().comemb_set_max_warps(int(self.n)))
+
+    def __exit__(self, *a):
+        if self.n:
+            _lib.check(_lib.load().comemb_set_max_warps(0))
+
+
 def o2_batch(node, ctx, walks, walk_off, seeds, lr, negative, window, table, alpha=1.0, mode=MODE_ORDERED, flags=0,
-             alias=None, base_seed=0, count_tokens=False):
+             alias=None, base_seed=0, count_tokens=False, max_warps=0):
     """train_o2 over a corpus.  node/ctx: float32 CUDA tensors [N, d] (in place).  walks: uint32 row tokens (flat),
     walk_off: int64 [n_walks+1], seeds: uint64 [n_walks] or None (-> F_SEED_HASH from base_seed)."""
     torch = _torch()
@@ -150,11 +170,12 @@ def o2_batch(node, ctx, walks, walk_off, seeds, lr, negative, window, table, alp
     if alias is not None:
         flags |= F_ALIAS
     tok = torch.zeros(1, dtype=torch.int64, device=node.device) if count_tokens else None
-    st = _lib.load().comemb_o2_walks(
-        _lib.ptr(node), _lib.ptr(ctx), node.shape[0], node.shape[1], _lib.ptr(walks), _lib.ptr(walk_off), n_walks,
-        _lib.ptr(seeds), int(base_seed), _lib.ptr(table), 0 if table is None else table.numel(), _lib.ptr(alias),
-        0 if alias is None else alias.numel() // 2, int(window), int(negative), float(lr), float(alpha), int(mode),
-        int(flags), _lib.ptr(tok), _lib.stream_ptr())
+    with _max_warps(max_warps):
+        st = _lib.load().comemb_o2_walks(
+            _lib.ptr(node), _lib.ptr(ctx), node.shape[0], node.shape[1], _lib.ptr(walks), _lib.ptr(walk_off), n_walks,
+            _lib.ptr(seeds), int(base_seed), _lib.ptr(table), 0 if table is None else table.numel(), _lib.ptr(alias),
+            0 if alias is None else alias.numel() // 2, int(window), int(negative), float(lr), float(alpha),
+            int(mode), int(flags), _lib.ptr(tok), _lib.stream_ptr())
     _lib.check(st)
     return int(tok.item()) if count_tokens else None
 
@@ -179,13 +200,21 @@ class HostO2Runner(object):
         self.d_off = torch.empty(max_walks + 1, dtype=torch.int64, device="cuda")
         self.d_seeds = torch.empty(max_walks, dtype=torch.int64, device="cuda")
 
+    def host_tables(self):
+        """numpy views of the runner's page-locked table buffers: a caller that keeps its tables here avoids the
+        pageable->pinned staging copy (pass these same arrays to run())."""
+        return self.h_node.numpy(), self.h_ctx.numpy()
+
     def run(self, node, ctx, walks, walk_off, seeds, lr, negative, window, alpha=1.0, mode=MODE_HOGWILD, flags=0):
         """node/ctx: numpy float32 [N,d] updated in place; walks uint32 flat; walk_off int64; seeds uint64.
         Returns (h2d_bytes, d2h_bytes)."""
         torch = _torch()
         nt, nw = walks.size, walk_off.size - 1
-        self.h_node.numpy()[...] = node
-        self.h_ctx.numpy()[...] = ctx
+        own = node is self.h_node.numpy() or (node.ctypes.data == self.h_node.data_ptr() and
+                                              ctx.ctypes.data == self.h_ctx.data_ptr())
+        if not own:
+            self.h_node.numpy()[...] = node
+            self.h_ctx.numpy()[...] = ctx
         self.h_walks.numpy()[:nt] = walks.view(np.int32)
         self.h_off.numpy()[:nw + 1] = walk_off
         self.h_seeds.numpy()[:nw] = seeds.view(np.int64)
@@ -199,14 +228,15 @@ class HostO2Runner(object):
         self.h_node.copy_(self.d_node, non_blocking=True)
         self.h_ctx.copy_(self.d_ctx, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        node[...] = self.h_node.numpy()
-        ctx[...] = self.h_ctx.numpy()
+        if not own:
+            node[...] = self.h_node.numpy()
+            ctx[...] = self.h_ctx.numpy()
         h2d = 2 * node.nbytes + nt * 4 + (nw + 1) * 8 + nw * 8
         return h2d, 2 * node.nbytes
 
 
 def o1_batch(node, edges, seeds, lr, negative, table, mode=MODE_ORDERED, flags=0, alias=None, base_seed=0,
-             edge_stride=0):
+             edge_stride=0, max_warps=0):
     """train_o1 over an edge list.  edges: uint32 CUDA tensor [E, 2] of row indices."""
     _lib.ensure_init()
     if seeds is None:
@@ -214,12 +244,13 @@ def o1_batch(node, edges, seeds, lr, negative, table, mode=MODE_ORDERED, flags=0
     if alias is not None:
         flags |= F_ALIAS
     n_edges = int(edges.numel() // 2)
-    st = _lib.load().comemb_o1_edges(
-        _lib.ptr(node), node.shape[0], node.shape[1], _lib.ptr(edges), n_edges, _lib.ptr(seeds), int(base_seed),
-        _lib.ptr(table), 0 if table is None else table.numel(), _lib.ptr(alias),
-        0 if alias is None else alias.numel() // 2, int(negative), float(lr), int(mode), int(flags),
-        int(edge_stride), _lib.stream_ptr())
-    _lib.check(st)
+    with _max_warps(max_warps):
+        st = _lib.load().comemb_o1_edges(
+            _lib.ptr(node), node.shape[0], node.shape[1], _lib.ptr(edges), n_edges, _lib.ptr(seeds), int(base_seed),
+            _lib.ptr(table), 0 if table is None else table.numel(), _lib.ptr(alias),
+            0 if alias is None else alias.numel() // 2, int(negative), float(lr), int(mode), int(flags),
+            int(edge_stride), _lib.stream_ptr())
+        _lib.check(st)
 
 
 def transpose_blocks(inv_cov):
@@ -339,6 +370,54 @@ def train_sg(py_node_embedding, py_negative_embedding, py_path, py_alpha, py_neg
     if not same:
         neg.writeback()
     return result
+
+
+def train_sg_twin(py_node_embedding, py_context_embedding, py_path, py_alpha, py_negative, py_window, py_table,
+                  py_centroid, py_inv_covariance_mat, py_pi, py_k, py_covariance_mat, py_lambda1=1.0, py_lambda2=0.0,
+                  py_size=None, py_work=None, py_work_o3=None, py_work1_o3=None, py_work2_o3=None,
+                  py_is_node_embedding=1):
+    """The reference's pure-Python fallback `train_sg` (utils/embedding.py:15-72) -- the semantics it falls back to
+    whenever the compiled fused kernel is absent, i.e. always at HEAD: no window shrinking, negatives redrawn with
+    `np.random.randint(len(table))` until they differ from both nodes of the pair (same draw order, so a seeded run
+    picks the same targets), exact sigmoid, vectorised target update.  The host walks the path and draws the
+    targets; the arithmetic runs in csrc (comemb_sg_twin)."""
+    torch = _torch()
+    node = _Borrowed(py_node_embedding)
+    same = py_context_embedding is py_node_embedding
+    ctx = node if same else _Borrowed(py_context_embedding)
+    table = np.asarray(py_table.cpu().numpy() if isinstance(py_table, torch.Tensor) else py_table)
+    rows, targets = [], []
+    n_table = table.shape[0]
+    for pos, nd in enumerate(py_path):  # embedding.py:29-52
+        if nd is None:
+            continue
+        start = max(0, pos - py_window)
+        for pos2, nd2 in enumerate(py_path[start: pos + py_window + 1], start):
+            if nd2 and not (pos2 == pos):
+                idx = [nd.index]
+                while len(idx) < py_negative + 1:
+                    w = int(table[np.random.randint(n_table)])
+                    if w != nd.index and w != nd2.index:
+                        idx.append(w)
+                rows.append(nd2.index)
+                targets.append(idx)
+    if rows:
+        # keep every device temporary referenced until the kernel has run
+        d_rows = _dev(np.asarray(rows, np.uint32), np.uint32)
+        d_tgt = _dev(np.asarray(targets, np.uint32).reshape(-1), np.uint32)
+        d_mu, d_inv = _const_dev(py_centroid, np.float32), _const_dev(py_inv_covariance_mat, np.float32)
+        d_pi = _const_dev(py_pi, np.float32)
+        st = _lib.load().comemb_sg_twin(
+            _lib.ptr(node.dev), _lib.ptr(ctx.dev), node.dev.shape[0], node.dev.shape[1], _lib.ptr(d_rows),
+            _lib.ptr(d_tgt), len(rows), int(py_negative), float(py_alpha), float(py_lambda1), float(py_lambda2),
+            _lib.ptr(d_mu), _lib.ptr(d_inv), _lib.ptr(d_pi), int(py_k), int(py_is_node_embedding), _lib.stream_ptr())
+        _lib.check(st)
+        torch.cuda.current_stream().synchronize()
+        del d_rows, d_tgt
+    node.writeback()
+    if not same:
+        ctx.writeback()
+    return len([w for w in py_path if w is not None])
 
 
 def _check_size(dev, py_size):

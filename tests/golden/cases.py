@@ -55,6 +55,18 @@ SG_CASES = {
 }
 
 
+# Python-twin fallback (utils/embedding.py:15-98): same input recipe as SG_CASES, different semantics
+TWIN_CASES = {
+    "twin_d128_ctx": dict(d=128, N=40, K=3, nw=3, L=10, W=2, neg=5, seed=600, lr=0.025, l1=1.0, l2=0.1, isnode=0),
+    "twin_d16_k4": dict(d=16, N=30, K=4, nw=3, L=20, W=4, neg=3, seed=601, lr=0.05, l1=0.7, l2=0.2, isnode=0),
+    "twin_d2_l2zero": dict(d=2, N=34, K=2, nw=4, L=20, W=3, neg=4, seed=602, lr=0.1, l1=1.0, l2=0.0, isnode=0),
+    "twin_d64_nodeemb_none": dict(d=64, N=30, K=3, nw=3, L=12, W=3, neg=4, seed=603, lr=0.05, l1=1.0, l2=0.3, isnode=1,
+                                  none_every=5),
+    "twin_tiny_table_duplicates": dict(d=8, N=6, K=2, nw=3, L=12, W=2, neg=5, seed=604, lr=0.1, l1=1.0, l2=0.0,
+                                       isnode=0),
+}
+
+
 def sg_inputs(c):
     rs = np.random.RandomState(c["seed"])
     d, N, K = c["d"], c["N"], c["K"]

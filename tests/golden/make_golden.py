@@ -81,6 +81,24 @@ def gen_sg(out):
         out[name + "/ret"] = np.int64(tot)
 
 
+def gen_twin(out):
+    """The reference's pure-Python fallback train_sg (utils/embedding.py:15-72), imported in place."""
+    import utils.embedding as E
+    assert E.train_sg.__module__ == "utils.embedding"  # the fallback, not a compiled kernel
+    for name, c in cases.TWIN_CASES.items():
+        node, ctx, table, mu, inv, pi, walks = cases.sg_inputs(c)
+        negemb = node if c["isnode"] else ctx
+        np.random.seed(c["seed"] + 7)
+        tot = 0
+        for path in walks:
+            tot += E.train_sg(node, negemb, to_path(path), c["lr"], c["neg"], c["W"], table, mu, inv, pi, c["K"], inv,
+                              py_lambda1=c["l1"], py_lambda2=c["l2"], py_size=c["d"],
+                              py_is_node_embedding=c["isnode"])
+        out[name + "/node"] = node
+        out[name + "/ctx"] = ctx
+        out[name + "/ret"] = np.int64(tot)
+
+
 class _FakeModel(object):
     pass
 
@@ -238,6 +256,8 @@ def main():
     gen_sg(sg_out)
     np.savez_compressed(os.path.join(HERE, "golden_sg.npz"), **sg_out)
     ref = O.load_ref("tuned", with_python_sources=True)
+    gen_twin(sg_out)
+    np.savez_compressed(os.path.join(HERE, "golden_sg.npz"), **sg_out)
     for fname, gen in (("golden_sgd.npz", lambda o: (gen_sgd(ref, o), gen_o3(o), gen_table(o))),):
         out = {}
         gen(out)
