@@ -23,6 +23,7 @@ int launch_sg_fused_hogwild(float *, float *, int, const uint32_t *, const int64
                             const float *, int, int, int, float, float, float, int, bool, cudaStream_t);
 void hogwild_set_tuning(int, int, int);
 void hogwild_set_max_warps(int64_t);
+extern bool g_force_generic_ordered;
 int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
                    const float *, const float *, const float *, int, int, cudaStream_t);
 int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const float *, const float *, const float *, int,
@@ -100,6 +101,7 @@ int comemb_get_lut(float *h_lut1000) {
 int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm) {
     if (centres_per_unit < 0 || max_walk_len < 0 || blocks_per_sm < 0) return COMEMB_E_ARG;
     hogwild_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm);
+    g_force_generic_ordered = (blocks_per_sm / 100) == 9;
     return 0;
 }
 

@@ -40,6 +40,22 @@ __device__ __forceinline__ uint64_t lcg_skip(uint64_t x, uint64_t n) {
     return (A * x + C) & LCG_MASK;
 }
 
+// x advanced by k = 0..NEG steps as affine maps with compile-time constants: lane k of a warp jumps straight to the
+// state its sample is drawn from.
+template <int NEG>
+struct LcgJump {  // x_{n+k} = A_k x_n + C_k  (mod 2^48)
+    uint64_t A[NEG + 1], C[NEG + 1];
+    __host__ __device__ constexpr LcgJump() : A{}, C{} {
+        uint64_t a = 1, c = 0;
+        for (int k = 0; k <= NEG; k++) {
+            A[k] = a & LCG_MASK;
+            C[k] = c & LCG_MASK;
+            c = (c * LCG_MUL + 11ULL) & LCG_MASK;
+            a = (a * LCG_MUL) & LCG_MASK;
+        }
+    }
+};
+
 // (next_random >> 16) % table_len  (pyx:133).  The state has 48 bits, so the dividend is a 32-bit value.
 struct TableMod {
     uint64_t len;    // table_len

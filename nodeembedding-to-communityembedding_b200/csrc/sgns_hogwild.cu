@@ -328,20 +328,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_kernel(
 //   * one transposed reduction + one lane-parallel sigma evaluation per pair;
 //   * duplicate samples inside a pair (which must see each other's update, pyx:146-147) are detected with one
 //     match.any and handled by a sequential path that re-reads rows from memory.
-template <int NEG>
-struct LcgJump {  // x_{n+k} = A_k x_n + C_k  (mod 2^48)
-    uint64_t A[NEG + 1], C[NEG + 1];
-    __host__ __device__ constexpr LcgJump() : A{}, C{} {
-        uint64_t a = 1, c = 0;
-        for (int k = 0; k <= NEG; k++) {
-            A[k] = a & LCG_MASK;
-            C[k] = c & LCG_MASK;
-            c = (c * LCG_MUL + 11ULL) & LCG_MASK;
-            a = (a * LCG_MUL) & LCG_MASK;
-        }
-    }
-};
-
 template <bool ATOMIC, int NEG, int MINB, bool HINT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_kernel(const O2Params P) {
     static_assert(NEG >= 1 && NEG <= 7, "positive + negatives must fit the 8 reduction slots");

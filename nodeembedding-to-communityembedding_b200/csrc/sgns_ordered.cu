@@ -174,6 +174,141 @@ __global__ void __launch_bounds__(32) o2_ordered_kernel(float *node, float *ctx,
     if (n_tokens && threadIdx.x == 0) *n_tokens += tokens;
 }
 
+// ---- o2 ORDERED, size == 128, register-resident ---------------------------------------------------------------------------
+// Same result as o2_ordered_kernel, several times faster: lane t keeps elements {t, t+32, t+64, t+96} of every row in
+// registers (that is the element->accumulator mapping of the reference's sdot: accumulator q = e mod 64 lives on lane
+// q mod 32), the NEG+1 rows of a pair are gathered together, the positive context row stays in registers across the
+// centre's window, samples are fetched one pair ahead.  Every floating-point operation and its association order is
+// the one of dot_refblas()/axpy_rows() above, so the tables stay bit-identical to the reference.
+struct Row4 {
+    float v0, v1, v2, v3;  // elements t, t+32, t+64, t+96
+};
+__device__ __forceinline__ Row4 ld_row4(const float *row, int lane) {
+    Row4 r;
+    r.v0 = row[lane]; r.v1 = row[lane + 32]; r.v2 = row[lane + 64]; r.v3 = row[lane + 96];
+    return r;
+}
+__device__ __forceinline__ void st_row4(float *row, int lane, const Row4 &r) {
+    row[lane] = r.v0; row[lane + 32] = r.v1; row[lane + 64] = r.v2; row[lane + 96] = r.v3;
+}
+// dot of two 128-element rows in the reference's order (see dot_refblas): value on every lane
+__device__ __forceinline__ float dot128_refblas(const Row4 &x, const Row4 &y, bool quirk) {
+    float a0 = fmaf(x.v2, y.v2, fmaf(x.v0, y.v0, 0.f));  // accumulator q = t      : elements t, t+64
+    float a1 = fmaf(x.v3, y.v3, fmaf(x.v1, y.v1, 0.f));  // accumulator q = t + 32 : elements t+32, t+96
+    a0 = a0 + __shfl_down_sync(FULL, a0, 8);
+    a1 = a1 + __shfl_down_sync(FULL, a1, 8);
+    float v = a0 + __shfl_down_sync(FULL, a0, 16);
+    v = v + a1;
+    v = v + __shfl_down_sync(FULL, a1, 16);
+    const float h = v + __shfl_down_sync(FULL, v, 4);
+    const float p = h + __shfl_down_sync(FULL, h, 1);
+    float my = p + __shfl_down_sync(FULL, p, 2);
+    my = __shfl_sync(FULL, my, 0);
+    if (!quirk) return my;  // (float)(0.0 + (double)my) == my
+    const double dot = (double)my;
+    return __double2float_rn(__hiloint2double(__double2hiint(dot), __float_as_int(my)));
+}
+__device__ __forceinline__ void fma_row4(Row4 &y, float a, const Row4 &x) {
+    y.v0 = fmaf(a, x.v0, y.v0); y.v1 = fmaf(a, x.v1, y.v1); y.v2 = fmaf(a, x.v2, y.v2); y.v3 = fmaf(a, x.v3, y.v3);
+}
+
+template <int NEG>
+__global__ void __launch_bounds__(32)
+    o2_ordered_d128_kernel(float *node, float *ctx, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
+                           const uint64_t *seeds, uint64_t base_seed, Sampler S, int window, float lr, float lambda,
+                           bool quirk, int64_t *n_tokens, const float *g_exp_table) {
+    constexpr int D = 128;
+    constexpr LcgJump<NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
+    __syncwarp();
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    int64_t tokens = 0;
+    for (int64_t w = 0; w < n_walks; w++) {
+        const uint32_t *path = walks + walk_off[w];
+        const int len = (int)min((int64_t)MAX_SENTENCE_LEN, walk_off[w + 1] - walk_off[w]);
+        uint64_t rnd = seeds ? seeds[w] : (splitmix64(base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        uint32_t tnext = (lane < NEG) ? S.table[table_slot((myA * rnd + myC) & LCG_MASK, S.mod)] : 0u;
+        rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+        for (int i = 0; i < len; i++) {  // pyx:494
+            const uint32_t wi = path[i];
+            if (wi == COMEMB_TOKEN_NONE) continue;
+            tokens++;
+            float *pos_ptr = ctx + (int64_t)wi * D;
+            Row4 cpos = ld_row4(pos_ptr, lane);
+            const int j1 = min(len, i + window + 1);
+            for (int j = max(0, i - window); j < j1; j++) {  // pyx:503
+                const uint32_t wj = path[j];
+                if (j == i || wj == COMEMB_TOKEN_NONE) continue;
+                float *row1_ptr = node + (int64_t)wj * D;
+                const Row4 x = ld_row4(row1_ptr, lane);
+                const uint32_t tmine = tnext;
+                tnext = (lane < NEG) ? S.table[table_slot((myA * rnd + myC) & LCG_MASK, S.mod)] : 0u;
+                rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+                uint32_t t[NEG];
+#pragma unroll
+                for (int k = 0; k < NEG; k++) t[k] = __shfl_sync(FULL, tmine, k);
+                bool anydup = false;
+#pragma unroll
+                for (int k = 1; k < NEG; k++)
+#pragma unroll
+                    for (int a = 0; a < k; a++) anydup = anydup || (t[a] == t[k]);
+                Row4 work = {0.f, 0.f, 0.f, 0.f};  // pyx:126
+                {  // positive target, pyx:129-131
+                    const float f = dot128_refblas(x, cpos, quirk);
+                    if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+                        const float g = __fmul_rn(__fmul_rn(1.f - lut[lut_index(f)], lr), lambda);
+                        fma_row4(work, g, cpos);  // pyx:146
+                        fma_row4(cpos, g, x);     // pyx:147 (registers; flushed when the centre ends)
+                    }
+                }
+                if (!anydup) {
+                    Row4 c[NEG];
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) c[k] = ld_row4(ctx + (int64_t)t[k] * D, lane);
+                    float f[NEG];
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) f[k] = dot128_refblas(x, c[k], quirk);
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) {
+                        if (t[k] == wi) continue;                                  // pyx:135-136
+                        if (f[k] <= -MAX_EXP_F || f[k] >= MAX_EXP_F) continue;    // pyx:141-142
+                        const float g = __fmul_rn(__fmul_rn(0.f - lut[lut_index(f[k])], lr), lambda);
+                        fma_row4(work, g, c[k]);
+                        fma_row4(c[k], g, x);
+                        st_row4(ctx + (int64_t)t[k] * D, lane, c[k]);
+                    }
+                } else {  // equal samples inside one pair: strictly one after the other, re-reading the row
+#pragma unroll 1
+                    for (int k = 0; k < NEG; k++) {
+                        const uint32_t tk = __shfl_sync(FULL, tmine, k);
+                        if (tk == wi) continue;
+                        float *cp = ctx + (int64_t)tk * D;
+                        Row4 c = ld_row4(cp, lane);
+                        const float f = dot128_refblas(x, c, quirk);
+                        if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
+                        const float g = __fmul_rn(__fmul_rn(0.f - lut[lut_index(f)], lr), lambda);
+                        fma_row4(work, g, c);
+                        fma_row4(c, g, x);
+                        st_row4(cp, lane, c);
+                    }
+                }
+                Row4 nx = {x.v0 + work.v0, x.v1 + work.v1, x.v2 + work.v2, x.v3 + work.v3};  // pyx:149
+                st_row4(row1_ptr, lane, nx);
+            }
+            st_row4(pos_ptr, lane, cpos);
+        }
+    }
+    if (n_tokens && lane == 0) *n_tokens += tokens;
+}
+
 __global__ void __launch_bounds__(32) o1_ordered_kernel(float *node, int size, const uint32_t *edges, int64_t n_edges,
                                                         const uint64_t *seeds, uint64_t base_seed, Sampler S,
                                                         int negative, float lr, bool quirk, const float *g_exp_table) {
@@ -356,11 +491,25 @@ __global__ void __launch_bounds__(32)
 
 }  // namespace
 
+bool g_force_generic_ordered = false;  // tests: comemb_set_tuning(.., .., 900) routes size 128 to the generic kernel
+
 // ---- launchers (called from capi.cu) -------------------------------------------------------------------------------------
 int launch_o2_ordered(float *node, float *ctx, int size, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
                       const uint64_t *seeds, uint64_t base_seed, const uint32_t *table, uint64_t table_len, int window,
                       int negative, float lr, float lambda, bool quirk, int64_t *n_tokens, cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
+    if (size == 128 && !g_force_generic_ordered) {  // register-resident fast path, same bits
+        switch (negative) {
+#define COMEMB_CASE(N)                                                                                             \
+    case N:                                                                                                        \
+        o2_ordered_d128_kernel<N><<<1, 32, 0, st>>>(node, ctx, walks, walk_off, n_walks, seeds, base_seed, S, window, \
+                                                    lr, lambda, quirk, n_tokens, comemb_lut_device());             \
+        return (int)cudaGetLastError();
+            COMEMB_CASE(1) COMEMB_CASE(2) COMEMB_CASE(3) COMEMB_CASE(4) COMEMB_CASE(5) COMEMB_CASE(6) COMEMB_CASE(7)
+#undef COMEMB_CASE
+            default: break;
+        }
+    }
     size_t smem = (EXP_TABLE_SIZE + (size_t)size) * sizeof(float);
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(o2_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
