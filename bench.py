@@ -206,6 +206,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+PARTITION = "replicated"
+
+
 def workload_config(n_gpus, atomic=True):
     if CFG["name"] == "youtube":
         wl = ("BASELINE configs[3] shape: synthetic power-law graph %.1fM nodes / %.0fM edges, d=%d, walk len %d, window "
@@ -219,7 +222,10 @@ def workload_config(n_gpus, atomic=True):
             "table_size": CFG["table_size"], "lr": CFG["lr"], "mode": "hogwild",
             "scatter": "red.global.add.v4.f32" if atomic else "plain 128-bit stores",
             "l2": "256 MiB flush write between timed steps; tables 2x%d MB" % (CFG["n"] * CFG["d"] * 4 // 1000000),
-            "parallelism": "replicated tables, walk stream sharded per GPU, NCCL all-reduce average every step"
+            "parallelism": ("replicated tables, walk stream sharded per GPU, NCCL all-reduce average every step"
+                            if PARTITION == "replicated" else
+                            "row-partitioned tables (contiguous row blocks per GPU), remote rows gathered and "
+                            "red.add-updated over NVLink inside the SGD kernel, no collective")
             if n_gpus > 1 else "single GPU"}
 
 
@@ -251,6 +257,12 @@ def run_ours(args):
     _lib.check(_lib.load().comemb_make_table(deg.ctypes.data, deg.size, 0.75, table.data_ptr(), table.numel(), None))
     node_h, ctx_h = init_tables_host(n, d)
     node, ctx = torch.from_numpy(node_h).cuda(), torch.from_numpy(ctx_h).cuda()
+    sharded = None
+    if args.partition == "rows" and world > 1:
+        from comemb_b200.sharded import ShardedTables
+        sharded = ShardedTables(n, d)
+        sharded.load_rows(node_h, ctx_h)
+        dist.barrier()
     rowptr, col = G.device()
     nws = CFG["walks_per_step"]
     walks = torch.empty((nws, L), dtype=torch.int32, device="cuda")
@@ -272,11 +284,14 @@ def run_ours(args):
                                         g_first, nws, walks.data_ptr(), lens.data_ptr(), stream.cuda_stream))
         if ev:
             ev[0].record(stream)
-        K.o2_batch(node, ctx, walks.reshape(-1), off, None, lr, neg, W, table, mode=K.MODE_HOGWILD, flags=flags,
-                   alias=alias, base_seed=1000003 * s + rank)
+        if sharded is not None:
+            sharded.o2(walks.reshape(-1), off, None, lr, neg, W, table, base_seed=1000003 * s + rank)
+        else:
+            K.o2_batch(node, ctx, walks.reshape(-1), off, None, lr, neg, W, table, mode=K.MODE_HOGWILD, flags=flags,
+                       alias=alias, base_seed=1000003 * s + rank)
         if ev:
             ev[1].record(stream)
-        if world > 1:
+        if world > 1 and sharded is None:
             replicas.average_tables([node, ctx], world=world)
 
     for s in range(args.warmup):
@@ -462,6 +477,9 @@ def main():
                     help="1 (default): scatter with red.global.add.v4.f32 (no lost updates); 0: plain stores")
     ap.add_argument("--workload", default="sbm", choices=["sbm", "youtube"],
                     help="sbm = BASELINE configs[1] (the judged line); youtube = configs[3] shape (HBM-bound regime)")
+    ap.add_argument("--partition", default="replicated", choices=["replicated", "rows"],
+                    help="N>1: replicated tables + NCCL averaging (default) or row-partitioned tables updated over "
+                         "NVLink from inside the SGD kernel (SURVEY 8e partition B)")
     ap.add_argument("--kernel", default="o2", choices=["o2", "o1", "o3"],
                     help="o2 = the judged metric; o1 / o3 = secondary kernels of the path (separate JSON line)")
     ap.add_argument("--alias", type=int, default=0, help="1: draw negatives from the alias table (Hogwild option)")
@@ -469,6 +487,8 @@ def main():
     ap.add_argument("--tuning", type=int, nargs=3, default=None, metavar=("CENTRES", "MAXLEN", "BLOCKS"),
                     help="comemb_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm) for experiments")
     args = ap.parse_args()
+    global PARTITION
+    PARTITION = args.partition
     if args.workload == "youtube":
         CFG.clear()
         CFG.update(CFG_YOUTUBE)

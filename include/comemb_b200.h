@@ -76,6 +76,22 @@ int comemb_o2_walks(float *d_node, float *d_ctx, int64_t n_rows, int size, const
                     int window, int negative, float lr, float lambda, int mode, uint32_t flags, int64_t *d_n_tokens,
                     void *stream);
 
+/* ---- o2 over ROW-PARTITIONED tables (HOGWILD, size 128, negative in 3..5, red.add scatter) -----------------------------
+ * Table row r lives in shard r / rows_per_shard at local row r % rows_per_shard.  h_node_shards / h_ctx_shards are HOST
+ * arrays of n_shards (<= 8) DEVICE pointers; a shard may be memory of a peer GPU of the same node mapped into this
+ * process (CUDA IPC) with peer access enabled (comemb_enable_peer_access): rows are then gathered and updated straight
+ * over NVLink from inside the SGD kernel -- no separate collective.  Other arguments as comemb_o2_walks. */
+int comemb_o2_walks_sharded(float *const *h_node_shards, float *const *h_ctx_shards, int n_shards,
+                            int64_t rows_per_shard, int size, const uint32_t *d_walks, const int64_t *d_walk_off,
+                            int64_t n_walks, const uint64_t *d_seeds, uint64_t base_seed, const uint32_t *d_table,
+                            uint64_t table_len, int window, int negative, float lr, float lambda, uint32_t flags,
+                            int64_t *d_n_tokens, void *stream);
+/* cudaIpcOpenMemHandle of a 64-byte handle exported by a peer process (torch: storage._share_cuda_()[1]) into the
+ * CURRENT device's context with lazy peer access; *h_out_ptr = mapped base + offset_bytes.  Synchronous. */
+int comemb_ipc_open(const void *h_handle64, int64_t offset_bytes, void **h_out_ptr);
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device (idempotent). */
+int comemb_enable_peer_access(int peer_device);
+
 /* ---- o1: replaces train_o1 (pyx:407-450) applied to a batch of edges, i.e. the worker loop of
  * Node2Vec.train (ADSCModel/node_embeddings.py:70-71) -------------------------------------------------------------------
  * d_edges : uint32 [n_edges, 2] row indices; per edge: update row e0 against target e1, then row e1 against the

@@ -26,6 +26,10 @@ SIGNATURES = {
     "comemb_error_string": (_c.c_char_p, [_i32]),
     "comemb_o2_walks": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _u64, _vp, _u64, _vp, _u32, _i32, _i32,
                                _f32, _f32, _i32, _u32, _vp, _vp]),
+    "comemb_o2_walks_sharded": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _u64, _vp, _u64, _i32, _i32, _f32,
+                                       _f32, _u32, _vp, _vp]),
+    "comemb_enable_peer_access": (_i32, [_i32]),
+    "comemb_ipc_open": (_i32, [_c.c_char_p, _i64, _vp]),
     "comemb_o1_edges": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _u64, _vp, _u64, _vp, _u32, _i32, _f32, _i32, _u32,
                                _i64, _vp]),
     "comemb_o3_batch": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _f64, _f32, _i32, _vp]),

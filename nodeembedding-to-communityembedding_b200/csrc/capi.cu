@@ -22,6 +22,9 @@ int launch_sg_fused_hogwild(float *, float *, int, const uint32_t *, const int64
                             const uint64_t *, uint64_t, const uint32_t *, uint64_t, const float *, const float *,
                             const float *, int, int, int, float, float, float, int, bool, cudaStream_t);
 void hogwild_set_tuning(int, int, int);
+int launch_o2_hogwild_sharded(float *const *, float *const *, int, int64_t, int, const uint32_t *, const int64_t *, int64_t,
+                              const uint64_t *, uint64_t, const uint32_t *, uint64_t, int, int, float, float, int64_t *,
+                              cudaStream_t);
 void hogwild_set_max_warps(int64_t);
 extern bool g_force_generic_ordered;
 int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
@@ -131,6 +134,50 @@ int comemb_o2_walks(float *d_node, float *d_ctx, int64_t n_rows, int size, const
                                  table_len, (flags & COMEMB_F_ALIAS) ? d_alias : nullptr, n_alias, window, negative, lr,
                                  lambda, (flags & COMEMB_F_ATOMIC) != 0, d_n_tokens, st);
     return COMEMB_E_ARG;
+}
+
+int comemb_o2_walks_sharded(float *const *h_node_shards, float *const *h_ctx_shards, int n_shards,
+                            int64_t rows_per_shard, int size, const uint32_t *d_walks, const int64_t *d_walk_off,
+                            int64_t n_walks, const uint64_t *d_seeds, uint64_t base_seed, const uint32_t *d_table,
+                            uint64_t table_len, int window, int negative, float lr, float lambda, uint32_t flags,
+                            int64_t *d_n_tokens, void *stream) {
+    REQUIRE_INIT();
+    if (!h_node_shards || !h_ctx_shards || n_shards < 1 || n_walks < 0 || window < 0 || negative < 0) return COMEMB_E_ARG;
+    for (int s = 0; s < n_shards && s < 8; s++)
+        if (!h_node_shards[s] || !h_ctx_shards[s]) return COMEMB_E_ARG;
+    if (n_walks > 0 && (!d_walks || !d_walk_off)) return COMEMB_E_ARG;
+    if (negative > 0 && (!d_table || table_len == 0)) return COMEMB_E_ARG;
+    if (!d_seeds && !(flags & COMEMB_F_SEED_HASH)) return COMEMB_E_ARG;
+    return launch_o2_hogwild_sharded(h_node_shards, h_ctx_shards, n_shards, rows_per_shard, size, d_walks, d_walk_off,
+                                     n_walks, d_seeds, base_seed, d_table, table_len, window, negative, lr, lambda,
+                                     d_n_tokens, (cudaStream_t)stream);
+}
+
+int comemb_ipc_open(const void *h_handle64, int64_t offset_bytes, void **h_out_ptr) {
+    // Map a peer process' allocation INTO THE CURRENT DEVICE's context (cudaIpcMemLazyEnablePeerAccess turns on peer
+    // access between the current device and the exporting device), so kernels launched here can dereference it.
+    if (!h_handle64 || !h_out_ptr || offset_bytes < 0) return COMEMB_E_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, sizeof(h));
+    void *base = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *h_out_ptr = static_cast<char *>(base) + offset_bytes;
+    return 0;
+}
+
+int comemb_enable_peer_access(int peer_device) {
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (peer_device == dev) return 0;
+    int can = 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return COMEMB_E_UNSUPPORTED;
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return 0;
+    }
+    return (int)e;
 }
 
 int comemb_o1_edges(float *d_node, int64_t n_rows, int size, const uint32_t *d_edges, int64_t n_edges,

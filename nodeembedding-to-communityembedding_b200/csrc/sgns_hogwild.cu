@@ -149,6 +149,11 @@ struct O2Params {
     int centres_per_unit, units_per_walk;
     int64_t *n_tokens;
     const float *glut;
+    // row-partitioned tables (n_shards > 0): rows [s*rows_per_shard, (s+1)*rows_per_shard) live in shard s, which may be
+    // memory of a peer GPU mapped over NVLink (CUDA IPC); n_shards == 0: one flat table at node/ctx
+    float *node_shard[8], *ctx_shard[8];
+    uint32_t rows_per_shard;
+    int n_shards;
 };
 
 // 8-slot transposed warp reduction.  Slot sums are formed by exactly the same lane pairings, level by level
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_kernel(
 //   * one transposed reduction + one lane-parallel sigma evaluation per pair;
 //   * duplicate samples inside a pair (which must see each other's update, pyx:146-147) are detected with one
 //     match.any and handled by a sequential path that re-reads rows from memory.
-template <bool ATOMIC, int NEG, int MINB, bool HINT>
+template <bool ATOMIC, int NEG, int MINB, bool HINT, bool SHARDED>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_kernel(const O2Params P) {
     static_assert(NEG >= 1 && NEG <= 7, "positive + negatives must fit the 8 reduction slots");
     constexpr int D = 128;
@@ -340,6 +345,21 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
     const int W = P.window;
     const float lr = P.lr, lambda = P.lambda;
     float *const node_l = P.node + 4 * lane, *const ctx_l = P.ctx + 4 * lane;  // this lane's float4 column
+    // row r of a table -> this lane's 16 bytes of it.  SHARDED: the owning shard's base (possibly peer memory)
+    auto NODE_ROW = [&](uint32_t r) -> float * {
+        if (SHARDED) {
+            const uint32_t sh = r / P.rows_per_shard;
+            return P.node_shard[sh] + (int64_t)(r - sh * P.rows_per_shard) * D + 4 * lane;
+        }
+        return node_l + (int64_t)r * D;
+    };
+    auto CTX_ROW = [&](uint32_t r) -> float * {
+        if (SHARDED) {
+            const uint32_t sh = r / P.rows_per_shard;
+            return P.ctx_shard[sh] + (int64_t)(r - sh * P.rows_per_shard) * D + 4 * lane;
+        }
+        return ctx_l + (int64_t)r * D;
+    };
     const Draw draw = P.draw;
     const uint64_t pol_keep = HINT ? l2_policy_evict_last() : 0, pol_stream = HINT ? l2_policy_evict_first() : 0;
     auto LDROW = [&](const float *p) { return HINT ? ldcg4_hint(p, pol_keep) : __ldcg(reinterpret_cast<const float4 *>(p)); };
@@ -397,14 +417,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
         for (int i = c0; i < c1; i++) {  // pyx:494
             const uint32_t wi = LDTOK(path + i);
             if (wi == COMEMB_TOKEN_NONE) continue;
-            float *pos_ptr = ctx_l + (int64_t)wi * D;
+            float *pos_ptr = CTX_ROW(wi);
             float4 cpos = LDROW(pos_ptr);
             float4 dpos = make_float4(0.f, 0.f, 0.f, 0.f);  // ATOMIC: accumulated delta of the positive row
             const int j1 = min(len, i + W + 1);
             for (int j = max(0, i - W); j < j1; j++) {  // pyx:503
                 const uint32_t wj = LDTOK(path + j);
                 if (j == i || wj == COMEMB_TOKEN_NONE) continue;
-                float *row1_ptr = node_l + (int64_t)wj * D;
+                float *row1_ptr = NODE_ROW(wj);
                 const float4 r1 = LDROW(row1_ptr);
                 const uint32_t tmine = tnext;  // this pair's samples (lane k holds sample k)
                 tnext = (lane < NEG) ? FETCH((myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
@@ -423,7 +443,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
                 if (!anydup) {
                     float4 c[NEG];
 #pragma unroll
-                    for (int k = 0; k < NEG; k++) c[k] = LDROW(ctx_l + (int64_t)t[k] * D);
+                    for (int k = 0; k < NEG; k++) c[k] = LDROW(CTX_ROW(t[k]));
                     float p[8];
                     p[0] = fmaf(r1.w, cpos.w, fmaf(r1.z, cpos.z, fmaf(r1.y, cpos.y, fmaf(r1.x, cpos.x, 0.f))));
 #pragma unroll
@@ -457,7 +477,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
                         const float g = __shfl_sync(FULL, gm, lane_of_p(k + 1));
                         work.x = fmaf(g, c[k].x, work.x); work.y = fmaf(g, c[k].y, work.y);  // pyx:146
                         work.z = fmaf(g, c[k].z, work.z); work.w = fmaf(g, c[k].w, work.w);
-                        float *cp = ctx_l + (int64_t)t[k] * D;
+                        float *cp = CTX_ROW(t[k]);
                         if (g != 0.f) {  // g == 0 <=> dropped or saturated target (sigma is never exactly 0 or 1)
                             if (ATOMIC) {
                                 red_add4(cp, make_float4(__fmul_rn(g, r1.x), __fmul_rn(g, r1.y), __fmul_rn(g, r1.z),
@@ -489,7 +509,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
                     for (int k = 0; k < NEG; k++) {
                         const uint32_t tk = __shfl_sync(FULL, tmine, k);
                         if (tk == wi) continue;  // pyx:135-136
-                        float *cp = ctx_l + (int64_t)tk * D;
+                        float *cp = CTX_ROW(tk);
                         const float4 c = LDROW(cp);
                         const float f = warp_sum_xor(fmaf(r1.w, c.w, fmaf(r1.z, c.z, fmaf(r1.y, c.y, fmaf(r1.x, c.x, 0.f)))));
                         if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;  // pyx:141-142
@@ -515,243 +535,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
             else
                 STROW(pos_ptr, cpos);
         }
-    }
-}
-
-// ---- o2, headline shape, software-pipelined ----------------------------------------------------------------------------
-// o2_hogwild_d128_kernel spends most of its time with every warp of an SM waiting on the same thing: the NEG+1 row
-// gathers of its current pair (ncu: long-scoreboard stalls, ~40 % issue utilisation).  Here the rows of pair p+1 are
-// copied global->shared with cp.async while pair p is being computed, so gather latency overlaps the dot/sigma/update
-// phase of the previous pair.  Every lane copies and later reads back only its own 16 bytes of each row, so no
-// cross-thread synchronisation is needed beyond cp.async.wait_group.
-//
-// Exactness inside a walk is kept: a prefetch is only issued when pair p+1 reads no row that pair p writes
-// (node row: same token; context rows: one match.any over {samples of p} u {samples of p+1}); otherwise, and for
-// the first pair of every centre, rows are loaded after the previous pair's stores, as in the unpipelined kernel.
-// Sample indices are fetched two pairs ahead.
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <bool ATOMIC, int NEG>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3) o2_hogwild_d128_pipe_kernel(const O2Params P) {
-    static_assert(NEG >= 1 && NEG <= 7, "positive + negatives must fit the 8 reduction slots");
-    constexpr int D = 128;
-    constexpr LcgJump<NEG> J{};
-    __shared__ float lut[EXP_TABLE_SIZE];
-    extern __shared__ float4 stage_dyn[];  // [WARPS_PER_BLOCK][2][NEG+1][32]: per warp 2 stages x (node row + NEG ctx rows)
-    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    float4(*stage)[NEG + 1][32] =
-        reinterpret_cast<float4(*)[NEG + 1][32]>(stage_dyn + (size_t)(threadIdx.x >> 5) * 2 * (NEG + 1) * 32);
-    const int W = P.window;
-    const float lr = P.lr, lambda = P.lambda;
-    float *const node_l = P.node + 4 * lane, *const ctx_l = P.ctx + 4 * lane;
-    const Draw draw = P.draw;
-    uint64_t myA = 1, myC = 0;
-#pragma unroll
-    for (int k = 0; k < NEG; k++)
-        if (lane == k) {
-            myA = J.A[k];
-            myC = J.C[k];
-        }
-    const int pi = ((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1);
-    const float my_label = pi == 0 ? 1.f : 0.f;
-    const unsigned cur_mask = (1u << NEG) - 1u, nxt_mask = cur_mask << 8;
-    const int64_t n_units = P.n_walks * P.units_per_walk;
-    const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
-
-    for (int64_t u = warp0; u < n_units; u += n_warps) {
-        const int64_t w = u / P.units_per_walk;
-        const int q = (int)(u - w * P.units_per_walk);
-        const uint32_t *path = P.walks + P.walk_off[w];
-        const int len = (int)min((int64_t)MAX_SENTENCE_LEN, P.walk_off[w + 1] - P.walk_off[w]);  // pyx:480
-        const int c0 = P.centres_per_unit ? q * P.centres_per_unit : 0;
-        const int c1 = P.centres_per_unit ? min(len, c0 + P.centres_per_unit) : len;
-        if (c0 >= len) continue;
-        uint64_t rnd = P.seeds ? P.seeds[w] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
-        if (q == 0 && P.n_tokens) {
-            int cnt = 0;
-            for (int i = lane; i < len; i += 32) cnt += (__ldg(path + i) != COMEMB_TOKEN_NONE);
-            cnt = __reduce_add_sync(FULL, cnt);
-            if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(P.n_tokens), (unsigned long long)cnt);
-        }
-        if (c0 > 0) {
-            int pairs = 0;
-            for (int i = lane; i < c0; i += 32) {
-                if (__ldg(path + i) == COMEMB_TOKEN_NONE) continue;
-                const int j1 = min(len, i + W + 1);
-                for (int j = max(0, i - W); j < j1; j++) pairs += (j != i && __ldg(path + j) != COMEMB_TOKEN_NONE);
-            }
-            pairs = __reduce_add_sync(FULL, pairs);
-            rnd = lcg_skip(rnd, (uint64_t)pairs * (uint64_t)NEG);
-        }
-        // sample indices run two pairs ahead of the pair being computed: tnext = next pair, tnext2 = the one after
-        uint32_t tnext = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
-        rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
-        uint32_t tnext2 = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
-        rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
-        int s = 0;  // stage holding (or about to hold) the CURRENT pair's rows
-
-        for (int i = c0; i < c1; i++) {  // pyx:494
-            const uint32_t wi = __ldg(path + i);
-            if (wi == COMEMB_TOKEN_NONE) continue;
-            float *pos_ptr = ctx_l + (int64_t)wi * D;
-            float4 cpos = __ldcg(reinterpret_cast<const float4 *>(pos_ptr));
-            float4 dpos = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int jb = min(len, i + W + 1);
-            int j = max(0, i - W);
-            while (j < jb && (j == i || __ldg(path + j) == COMEMB_TOKEN_NONE)) j++;
-            bool pre = false;  // are the current pair's rows in stage[s]?
-            while (j < jb) {   // pyx:503
-                const uint32_t wj = __ldg(path + j);
-                int jn = j + 1;
-                while (jn < jb && (jn == i || __ldg(path + jn) == COMEMB_TOKEN_NONE)) jn++;
-                const uint32_t tmine = tnext;
-                tnext = tnext2;
-                tnext2 = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
-                rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
-                // one match over {this pair's samples (lanes 0..), next pair's samples (lanes 8..)}
-                const uint32_t tn_up = __shfl_up_sync(FULL, tnext, 8);
-                const uint32_t probe = (lane >= 8 && lane < 8 + NEG) ? tn_up : (lane < NEG ? tmine : 0xFFFFFF00u + lane);
-                const unsigned same = __match_any_sync(FULL, probe);
-                const bool is_cur = lane < NEG;
-                const bool anydup = __any_sync(FULL, is_cur && ((same & cur_mask) & ((same & cur_mask) - 1u)) != 0u);
-                const bool has_next = jn < jb;
-                bool conflict = true;
-                uint32_t wjn = 0;
-                if (has_next) {
-                    wjn = __ldg(path + jn);
-                    conflict = (wjn == wj) || __any_sync(FULL, is_cur && (same & nxt_mask) != 0u);
-                }
-                const bool pre_next = has_next && !conflict;
-                if (pre_next) {  // gather the next pair's rows into the other stage while this pair is computed
-                    cp_async16(&stage[s ^ 1][0][lane], node_l + (int64_t)wjn * D);
-#pragma unroll
-                    for (int k = 0; k < NEG; k++)
-                        cp_async16(&stage[s ^ 1][1 + k][lane], ctx_l + (int64_t)__shfl_sync(FULL, tnext, k) * D);
-                }
-                cp_async_commit();  // (possibly empty) group: keeps the wait_group arithmetic uniform
-                float *row1_ptr = node_l + (int64_t)wj * D;
-                float4 r1;
-                float4 work = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pre) {
-                    cp_async_wait<1>();  // everything but the group just committed has landed
-                    r1 = stage[s][0][lane];
-                } else {
-                    r1 = __ldcg(reinterpret_cast<const float4 *>(row1_ptr));
-                }
-                if (!anydup) {
-                    uint32_t t[NEG];
-                    float4 c[NEG];
-#pragma unroll
-                    for (int k = 0; k < NEG; k++) {
-                        t[k] = __shfl_sync(FULL, tmine, k);
-                        if (pre)
-                            c[k] = stage[s][1 + k][lane];
-                        else
-                            c[k] = __ldcg(reinterpret_cast<const float4 *>(ctx_l + (int64_t)t[k] * D));
-                    }
-                    float p[8];
-                    p[0] = fmaf(r1.w, cpos.w, fmaf(r1.z, cpos.z, fmaf(r1.y, cpos.y, fmaf(r1.x, cpos.x, 0.f))));
-#pragma unroll
-                    for (int k = 0; k < 7; k++)
-                        p[k + 1] = k < NEG ? fmaf(r1.w, c[k < NEG ? k : 0].w,
-                                                  fmaf(r1.z, c[k < NEG ? k : 0].z,
-                                                       fmaf(r1.y, c[k < NEG ? k : 0].y,
-                                                            fmaf(r1.x, c[k < NEG ? k : 0].x, 0.f))))
-                                           : 0.f;
-                    const float fm = reduce8_transposed(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], lane);
-                    bool live = pi == 0;
-#pragma unroll
-                    for (int k = 0; k < NEG; k++) live = live || (pi == k + 1 && t[k] != wi);
-                    float gm = 0.f;
-                    if (live && fm > -MAX_EXP_F && fm < MAX_EXP_F)  // pyx:141-144
-                        gm = __fmul_rn(__fmul_rn(my_label - lut[lut_index(fm)], lr), lambda);
-                    {
-                        const float g = __shfl_sync(FULL, gm, lane_of_p(0));
-                        work.x = fmaf(g, cpos.x, work.x); work.y = fmaf(g, cpos.y, work.y);
-                        work.z = fmaf(g, cpos.z, work.z); work.w = fmaf(g, cpos.w, work.w);
-                        if (ATOMIC) {
-                            dpos.x = fmaf(g, r1.x, dpos.x); dpos.y = fmaf(g, r1.y, dpos.y);
-                            dpos.z = fmaf(g, r1.z, dpos.z); dpos.w = fmaf(g, r1.w, dpos.w);
-                        }
-                        cpos.x = fmaf(g, r1.x, cpos.x); cpos.y = fmaf(g, r1.y, cpos.y);
-                        cpos.z = fmaf(g, r1.z, cpos.z); cpos.w = fmaf(g, r1.w, cpos.w);
-                    }
-#pragma unroll
-                    for (int k = 0; k < NEG; k++) {
-                        const float g = __shfl_sync(FULL, gm, lane_of_p(k + 1));
-                        work.x = fmaf(g, c[k].x, work.x); work.y = fmaf(g, c[k].y, work.y);
-                        work.z = fmaf(g, c[k].z, work.z); work.w = fmaf(g, c[k].w, work.w);
-                        float *cp = ctx_l + (int64_t)t[k] * D;
-                        if (g != 0.f) {
-                            if (ATOMIC)
-                                red_add4(cp, make_float4(__fmul_rn(g, r1.x), __fmul_rn(g, r1.y), __fmul_rn(g, r1.z),
-                                                         __fmul_rn(g, r1.w)));
-                            else
-                                st4(cp, make_float4(fmaf(g, r1.x, c[k].x), fmaf(g, r1.y, c[k].y), fmaf(g, r1.z, c[k].z),
-                                                    fmaf(g, r1.w, c[k].w)));
-                        }
-                    }
-                } else {
-                    // sequential path: every target re-reads its row after the previous target's write
-                    {
-                        const float f = warp_sum_xor(
-                            fmaf(r1.w, cpos.w, fmaf(r1.z, cpos.z, fmaf(r1.y, cpos.y, fmaf(r1.x, cpos.x, 0.f)))));
-                        if (f > -MAX_EXP_F && f < MAX_EXP_F) {
-                            const float g = sgns_g(f, 1.f, lr, lambda, lut);
-                            work.x = fmaf(g, cpos.x, work.x); work.y = fmaf(g, cpos.y, work.y);
-                            work.z = fmaf(g, cpos.z, work.z); work.w = fmaf(g, cpos.w, work.w);
-                            if (ATOMIC) {
-                                dpos.x = fmaf(g, r1.x, dpos.x); dpos.y = fmaf(g, r1.y, dpos.y);
-                                dpos.z = fmaf(g, r1.z, dpos.z); dpos.w = fmaf(g, r1.w, dpos.w);
-                            }
-                            cpos.x = fmaf(g, r1.x, cpos.x); cpos.y = fmaf(g, r1.y, cpos.y);
-                            cpos.z = fmaf(g, r1.z, cpos.z); cpos.w = fmaf(g, r1.w, cpos.w);
-                        }
-                    }
-#pragma unroll 1
-                    for (int k = 0; k < NEG; k++) {
-                        const uint32_t tk = __shfl_sync(FULL, tmine, k);
-                        if (tk == wi) continue;
-                        float *cp = ctx_l + (int64_t)tk * D;
-                        const float4 c = __ldcg(reinterpret_cast<const float4 *>(cp));
-                        const float f = warp_sum_xor(fmaf(r1.w, c.w, fmaf(r1.z, c.z, fmaf(r1.y, c.y, fmaf(r1.x, c.x, 0.f)))));
-                        if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
-                        const float g = sgns_g(f, 0.f, lr, lambda, lut);
-                        work.x = fmaf(g, c.x, work.x); work.y = fmaf(g, c.y, work.y);
-                        work.z = fmaf(g, c.z, work.z); work.w = fmaf(g, c.w, work.w);
-                        if (ATOMIC)
-                            red_add4(cp, make_float4(__fmul_rn(g, r1.x), __fmul_rn(g, r1.y), __fmul_rn(g, r1.z),
-                                                     __fmul_rn(g, r1.w)));
-                        else
-                            st4(cp, make_float4(fmaf(g, r1.x, c.x), fmaf(g, r1.y, c.y), fmaf(g, r1.z, c.z),
-                                                fmaf(g, r1.w, c.w)));
-                    }
-                }
-                if (ATOMIC)
-                    red_add4(row1_ptr, work);
-                else
-                    st4(row1_ptr, make_float4(r1.x + work.x, r1.y + work.y, r1.z + work.z, r1.w + work.w));
-                pre = pre_next;
-                s ^= 1;
-                j = jn;
-            }
-            if (ATOMIC)
-                red_add4(pos_ptr, dpos);
-            else
-                st4(pos_ptr, cpos);
-        }
-        cp_async_wait<0>();
     }
 }
 
@@ -891,25 +674,17 @@ int launch_o2_t(const O2Params &P, bool atomic, cudaStream_t st) {
 template <int NEG>
 int launch_o2_d128(const O2Params &P, bool atomic, cudaStream_t st) {
     const int64_t n_units = P.n_walks * P.units_per_walk;
-    if (g_tuning.variant == 6) {  // experiment: software-pipelined kernel
-        const size_t smem = (size_t)WARPS_PER_BLOCK * 2 * (NEG + 1) * 32 * sizeof(float4);
-        if (atomic) {
-            auto k = o2_hogwild_d128_pipe_kernel<true, NEG>;
-            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<grid_for(k, n_units, smem), WARPS_PER_BLOCK * 32, smem, st>>>(P);
-        } else {
-            auto k = o2_hogwild_d128_pipe_kernel<false, NEG>;
-            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<grid_for(k, n_units, smem), WARPS_PER_BLOCK * 32, smem, st>>>(P);
-        }
-        return (int)cudaGetLastError();
-    }
     const bool hint = g_tuning.variant == 5;  // experiment: L2 eviction-priority hints
 #define COMEMB_LAUNCH(ATOM, HINT)                                            \
     do {                                                                     \
-        auto k = o2_hogwild_d128_kernel<ATOM, NEG, 3, HINT>;                 \
+        auto k = o2_hogwild_d128_kernel<ATOM, NEG, 3, HINT, false>;          \
         k<<<grid_for(k, n_units), WARPS_PER_BLOCK * 32, 0, st>>>(P);         \
     } while (0)
+    if (P.n_shards > 0) {  // row-partitioned tables: always red.add (remote rows are updated over NVLink)
+        auto k = o2_hogwild_d128_kernel<true, NEG, 3, false, true>;
+        k<<<grid_for(k, n_units), WARPS_PER_BLOCK * 32, 0, st>>>(P);
+        return (int)cudaGetLastError();
+    }
     if (atomic) {
         if (hint) COMEMB_LAUNCH(true, true); else COMEMB_LAUNCH(true, false);
     } else {
@@ -961,6 +736,8 @@ int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, 
     }
     P.n_tokens = n_tokens;
     P.glut = comemb_lut_device();
+    P.n_shards = 0;
+    P.rows_per_shard = 1;
     const bool vec = (size % 4) == 0;
     if (size == 128 && g_tuning.variant != 9) {  // the headline shape (variant 9 forces the generic kernel: tests)
         switch (negative) {
@@ -990,4 +767,33 @@ int launch_o1_hogwild(float *node, int size, const uint32_t *edges, int64_t n_ed
     if (size <= 128) return vec ? launch_o1_t<1, true>(P, atomic, st) : launch_o1_t<1, false>(P, atomic, st);
     if (size <= 256) return vec ? launch_o1_t<2, true>(P, atomic, st) : launch_o1_t<2, false>(P, atomic, st);
     return vec ? launch_o1_t<4, true>(P, atomic, st) : launch_o1_t<4, false>(P, atomic, st);
+}
+
+// Row-partitioned o2 (SURVEY 8e partition B): tables split into n_shards contiguous row blocks, each possibly on a
+// peer GPU (pointers mapped through CUDA IPC); the kernel gathers rows and scatters red.add updates straight over
+// NVLink -- the exchange is fused into the SGD kernel, there is no separate collective.
+int launch_o2_hogwild_sharded(float *const *node_shards, float *const *ctx_shards, int n_shards, int64_t rows_per_shard,
+                              int size, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
+                              const uint64_t *seeds, uint64_t base_seed, const uint32_t *table, uint64_t table_len,
+                              int window, int negative, float lr, float lambda, int64_t *n_tokens, cudaStream_t st) {
+    if (size != 128 || n_shards < 1 || n_shards > 8 || rows_per_shard <= 0 || rows_per_shard > 0xFFFFFFFFLL)
+        return COMEMB_E_UNSUPPORTED;
+    if (n_walks == 0) return 0;
+    O2Params P;
+    P.node = node_shards[0]; P.ctx = ctx_shards[0]; P.d = size; P.walks = walks; P.walk_off = walk_off;
+    P.n_walks = n_walks; P.seeds = seeds; P.base_seed = base_seed;
+    P.draw = Draw{table, make_table_mod(table_len), nullptr, 0};
+    P.window = window; P.negative = negative; P.lr = lr; P.lambda = lambda;
+    P.centres_per_unit = 0; P.units_per_walk = 1; P.n_tokens = n_tokens; P.glut = comemb_lut_device();
+    P.n_shards = n_shards; P.rows_per_shard = (uint32_t)rows_per_shard;
+    for (int s = 0; s < 8; s++) {
+        P.node_shard[s] = s < n_shards ? node_shards[s] : nullptr;
+        P.ctx_shard[s] = s < n_shards ? ctx_shards[s] : nullptr;
+    }
+    switch (negative) {
+        case 3: return launch_o2_d128<3>(P, true, st);
+        case 4: return launch_o2_d128<4>(P, true, st);
+        case 5: return launch_o2_d128<5>(P, true, st);
+        default: return COMEMB_E_UNSUPPORTED;
+    }
 }

@@ -596,3 +596,27 @@ def test_train_sg_twin_vs_reference_python_fallback(K, golden, name):
     assert np.abs(node - g[name + "/node"]).max() <= 1e-5 * max(1.0, np.abs(g[name + "/node"]).max())
     assert np.abs(ctx - g[name + "/ctx"]).max() <= 1e-5 * max(1.0, np.abs(g[name + "/ctx"]).max())
     assert np.abs(g[name + "/node"] - cases.sg_inputs(c)[0]).max() > 1e-3
+
+
+# ---- row-partitioned tables (SURVEY 8e partition B): the sharded addressing on one GPU ---------------------------------------
+def test_o2_sharded_addressing_equals_flat_tables(K):
+    """Same walks, same seeds: tables split into 3 row shards (all on this GPU) vs one flat table, both with red.add
+    scatter, one walk per launch (no races): bit-identical.  The multi-process NVLink path is exercised by
+    scripts/sharded_p2p_check.py under `gpurun --gpus 2`."""
+    import torch
+    from comemb_b200.sharded import ShardedTables
+    c = cases.O2_CASES["o2_d128_sbm_shape"]
+    node, ctx, table, walks = cases.o2_inputs(c)
+    seeds = O.seeds_from_numpy(np.random.RandomState(9), len(walks))
+    st = ShardedTables(c["N"], 128, local_only=True, n_local_shards=3)
+    assert st.rps == 334
+    st.load_rows(node, ctx)
+    dn, dc, dt = dev(node), dev(ctx), dev(table)
+    for w, s in list(zip(walks, seeds))[:12]:
+        off = dev(np.array([0, len(w)], np.int64))
+        sd = dev(np.array([s], np.uint64))
+        K.o2_batch(dn, dc, dev(w), off, sd, c["lr"], c["neg"], c["W"], dt, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC)
+        st.o2(dev(w), off, sd, c["lr"], c["neg"], c["W"], dt)
+    gn, gc = st.gather()
+    assert torch.equal(gn, dn) and torch.equal(gc, dc)
+    assert not np.array_equal(host(dn), node)

@@ -52,3 +52,12 @@ def test_shard_range_partitions_everything():
             assert parts[0][0] == 0 and sum(c for _, c in parts) == total
             assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_rows_per_shard():
+    from comemb_b200.sharded import rows_per_shard
+    assert rows_per_shard(100000, 8) == 12500 and rows_per_shard(100001, 8) == 12501 and rows_per_shard(5, 8) == 1
+    for n in (1, 34, 100000, 50000000):
+        for w in (1, 2, 4, 8):
+            r = rows_per_shard(n, w)
+            assert r * w >= n and (r - 1) * w < n
