@@ -432,7 +432,41 @@ def run_secondary(args):
             ts.append(e0.elapsed_time(e1))
         return sum(ts) / len(ts)
 
-    if args.kernel == "o1":
+    if args.kernel == "sg":  # the legacy fused pass (o3 gradient + SGNS per pair), Hogwild, one-hot pi
+        from comemb_b200.utils import graph_utils as gu
+        L, W, Kc = CFG["L"], CFG["W"], CFG.get("blocks", 50)
+        deg = np.ascontiguousarray(np.diff(G.rowptr), np.float64)
+        table = torch.empty(CFG["table_size"], dtype=torch.int32, device="cuda")
+        _lib.check(_lib.load().comemb_make_table(deg.ctypes.data, deg.size, 0.75, table.data_ptr(), table.numel(), None))
+        nw = args.sg_walks
+        walks, lens = gu.build_deepwalk_corpus(G, 1, L, alpha=0.0, seed=5, mode=gu.MODE_HOGWILD, return_device=True,
+                                               first_walk=0, n_out=nw)
+        off = torch.arange(nw + 1, dtype=torch.int64, device="cuda") * L
+        rs = np.random.RandomState(0)
+        mu = torch.from_numpy(rs.uniform(-0.5, 0.5, (Kc, d)).astype(np.float32)).cuda()
+        a = rs.normal(size=(Kc, d, d)).astype(np.float32) * 0.05
+        inv = torch.from_numpy(a + np.eye(d, dtype=np.float32)).cuda()
+        pi_h = np.zeros((n, Kc), np.float32)
+        pi_h[np.arange(n), block % Kc] = 1.0
+        pi = torch.from_numpy(pi_h).cuda()
+        ctx = torch.zeros_like(node)
+        rw = torch.from_numpy(rs.randint(0, W, nw * L).astype(np.int32)).cuda() if args.sg_shrink else None
+        ms = timed(lambda: K.sg_batch(node, ctx, walks.reshape(-1), off, rw, None, 0.025, neg, W, table, mu, inv, pi,
+                                      1.0, 0.1, 0, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC, base_seed=3))
+        lens_h = lens.cpu().numpy()
+        if rw is None:
+            pairs = sum(pairs_of_len(int(l), W) for l in lens_h[:1]) * nw
+        else:
+            r = rw.cpu().numpy().reshape(nw, L)
+            i = np.arange(L)[None, :]
+            pairs = int((np.minimum(L, i + W + 1 - r) - np.maximum(0, i - W + r) - 1).clip(0).sum())
+        v = pairs / (ms * 1e-3)
+        out.update({"metric": "fused_sg_pair_updates_per_sec", "value": v, "unit": "pair-updates/s", "ms_per_step": ms,
+                    "walks": nw, "pairs": pairs, "K": Kc, "pi": "one-hot", "window_shrink": bool(args.sg_shrink),
+                    "roofline": {"bound": "hbm (SGNS part) / fp32-FMA+L2 (o3 part)", "achieved": v * B_PAIR / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": v * B_PAIR / 1e9 / peak,
+                                 "o3_gflops": v * 2 * d * d / 1e9}})
+    elif args.kernel == "o1":
         deg = np.ascontiguousarray(np.diff(G.rowptr), np.float64)
         table = torch.empty(CFG["table_size"], dtype=torch.int32, device="cuda")
         _lib.check(_lib.load().comemb_make_table(deg.ctypes.data, deg.size, 0.75, table.data_ptr(), table.numel(), None))
@@ -480,8 +514,10 @@ def main():
     ap.add_argument("--partition", default="replicated", choices=["replicated", "rows"],
                     help="N>1: replicated tables + NCCL averaging (default) or row-partitioned tables updated over "
                          "NVLink from inside the SGD kernel (SURVEY 8e partition B)")
-    ap.add_argument("--kernel", default="o2", choices=["o2", "o1", "o3"],
+    ap.add_argument("--kernel", default="o2", choices=["o2", "o1", "o3", "sg"],
                     help="o2 = the judged metric; o1 / o3 = secondary kernels of the path (separate JSON line)")
+    ap.add_argument("--sg-walks", type=int, default=20000)
+    ap.add_argument("--sg-shrink", type=int, default=0, help="1: random window shrinking like the legacy train_sg")
     ap.add_argument("--alias", type=int, default=0, help="1: draw negatives from the alias table (Hogwild option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tuning", type=int, nargs=3, default=None, metavar=("CENTRES", "MAXLEN", "BLOCKS"),

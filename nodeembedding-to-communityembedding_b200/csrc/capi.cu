@@ -27,6 +27,8 @@ int launch_o2_hogwild_sharded(float *const *, float *const *, int, int64_t, int,
                               cudaStream_t);
 void hogwild_set_max_warps(int64_t);
 extern bool g_force_generic_ordered;
+extern bool g_force_generic_fused;
+extern int64_t g_fused_n_rows;
 int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
                    const float *, const float *, const float *, int, int, cudaStream_t);
 int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const float *, const float *, const float *, int,
@@ -105,6 +107,7 @@ int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm)
     if (centres_per_unit < 0 || max_walk_len < 0 || blocks_per_sm < 0) return COMEMB_E_ARG;
     hogwild_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm);
     g_force_generic_ordered = (blocks_per_sm / 100) == 9;
+    g_force_generic_fused = (blocks_per_sm / 100) == 9;
     return 0;
 }
 
@@ -234,6 +237,7 @@ int comemb_sg_fused(float *d_node, float *d_negemb, int64_t n_rows, int size, co
         return launch_sg_fused_ordered(d_node, d_negemb, size, d_walks, d_walk_off, n_walks, d_reduced_windows, d_seeds,
                                        base_seed, d_table, table_len, d_mu, d_inv_cov, d_pi, K, window, negative, lr,
                                        lambda1, lambda2, is_node_embedding, !(flags & COMEMB_F_DOT_FLOAT), st);
+    g_fused_n_rows = n_rows;
     if (mode == COMEMB_MODE_HOGWILD)
         return launch_sg_fused_hogwild(d_node, d_negemb, size, d_walks, d_walk_off, n_walks, d_reduced_windows, d_seeds,
                                        base_seed, d_table, table_len, d_mu, d_inv_cov, d_pi, K, window, negative, lr,

@@ -85,6 +85,30 @@ __device__ __forceinline__ float warp_sum_xor(float v) {
     return v;
 }
 
+// 8-slot transposed warp reduction.  Slot sums are formed by exactly the same lane pairings, level by level
+// (xor 16, 8, 4, 2, 1), as eight independent xor-butterflies would use -- so every slot total is bit-identical to
+// warp_sum_xor() of that slot -- but each level halves the number of live slots: 9 shuffles instead of 40.
+// On return lane l holds the total of slot (l >> 2) & 7.
+__device__ __forceinline__ float reduce8_transposed(float p0, float p1, float p2, float p3, float p4, float p5,
+                                                    float p6, float p7, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const float q0 = (b4 ? p4 : p0) + __shfl_xor_sync(FULL, b4 ? p0 : p4, 16);
+    const float q1 = (b4 ? p5 : p1) + __shfl_xor_sync(FULL, b4 ? p1 : p5, 16);
+    const float q2 = (b4 ? p6 : p2) + __shfl_xor_sync(FULL, b4 ? p2 : p6, 16);
+    const float q3 = (b4 ? p7 : p3) + __shfl_xor_sync(FULL, b4 ? p3 : p7, 16);
+    const float r0 = (b3 ? q2 : q0) + __shfl_xor_sync(FULL, b3 ? q0 : q2, 8);
+    const float r1 = (b3 ? q3 : q1) + __shfl_xor_sync(FULL, b3 ? q1 : q3, 8);
+    float t = (b2 ? r1 : r0) + __shfl_xor_sync(FULL, b2 ? r0 : r1, 4);
+    t += __shfl_xor_sync(FULL, t, 2);
+    t += __shfl_xor_sync(FULL, t, 1);
+    return t;
+}
+
+// p_i ends on the four lanes whose bits (b4,b3,b2) spell i: level 16 keeps by i>>2, level 8 by (i>>1)&1, level 4 by i&1
+__host__ __device__ constexpr int lane_of_p(int i) {
+    return ((i >> 2) << 4) | (((i >> 1) & 1) << 3) | ((i & 1) << 2);
+}
+
 // splitmix64: per-unit seed derivation for COMEMB_F_SEED_HASH and the Hogwild walker.
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;
