@@ -11,16 +11,30 @@ from ..utils import training_sdg_inner as K
 
 
 class Community2Vec(object):
-    def __init__(self, model, lr, reg_covar=0):
+    def __init__(self, model, lr, reg_covar=0, gmm_backend="sklearn"):
+        """gmm_backend: "sklearn" = the reference's host fit (:18, bit-compatible inputs for o3); "device" = the same EM
+        on the GPU (gmm_device.DeviceGaussianMixture: library GEMMs, tables never leave HBM)."""
         self.lr = lr
         self.reg_covar = reg_covar
         self.k = model.k
         self.g_mixture = None
+        self.gmm_backend = gmm_backend
 
     def fit(self, model):
-        import sklearn.mixture as mixture
         import torch
         log.info("Fitting: {} communities".format(model.k))
+        if self.gmm_backend == "device":
+            from .gmm_device import DeviceGaussianMixture
+            gm = DeviceGaussianMixture(n_components=model.k, reg_covar=self.reg_covar, n_init=10)
+            x = model.node_embedding.detach()
+            gm.fit(x)
+            self.g_mixture = gm
+            model.centroid = gm.means_.float().contiguous()
+            model.covariance_mat = gm.covariances_.float().contiguous()
+            model.inv_covariance_mat = torch.linalg.inv(model.covariance_mat).contiguous()
+            model.pi = gm.predict_proba(x).float().contiguous()
+            return
+        import sklearn.mixture as mixture
         if self.g_mixture is None:
             self.g_mixture = mixture.GaussianMixture(n_components=model.k, reg_covar=self.reg_covar,
                                                      covariance_type='full', n_init=10)

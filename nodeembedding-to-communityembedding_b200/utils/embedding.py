@@ -59,6 +59,22 @@ def paths_to_rows(model, paths):
     flat, off = [], [0]
     ids, rows, probs = model.id_index()
     any_ds = bool((probs < 1.0).any())
+    if isinstance(paths, RepeatCorpusNTimes) and isinstance(paths.corpus, np.ndarray) and paths.corpus.ndim == 2:
+        paths = np.concatenate([paths.corpus] * paths.n) if paths.n != 1 else paths.corpus
+    if isinstance(paths, np.ndarray) and paths.ndim == 2 and paths.dtype.kind in "iu":
+        # a rectangular corpus (edge list, fixed-length walks): map every token at once
+        a = paths.astype(np.int64, copy=False)
+        pos = np.searchsorted(ids, a.ravel())
+        pos[pos >= ids.size] = 0
+        keep = ids[pos] == a.ravel()
+        if any_ds:  # one random_sample() per in-vocabulary token with probability < 1, in corpus order
+            p = probs[pos]
+            cand = np.flatnonzero(keep & (p < 1.0))
+            keep[cand] = p[cand] >= np.random.random_sample(cand.size)
+        lens = keep.reshape(a.shape).sum(1)
+        offs = np.zeros(a.shape[0] + 1, np.int64)
+        np.cumsum(lens, out=offs[1:])
+        return np.ascontiguousarray(rows[pos[keep]].astype(np.uint32)), offs
     for path in paths:
         a = np.asarray(path, dtype=np.int64).ravel()
         pos = np.searchsorted(ids, a)

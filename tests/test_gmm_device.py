@@ -1,0 +1,93 @@
+"""N1: the device GMM (ADSCModel/gmm_device.py) against sklearn's own EM, step by step from identical initial
+responsibilities (sklearn's private `_initialize` / `_e_step` / `_m_step` driven by hand).  Runs on CPU tensors here
+and on the GPU under -m gpu."""
+import numpy as np
+import pytest
+
+
+def _blobs(n, d, k, seed):
+    rs = np.random.RandomState(seed)
+    centres = rs.normal(size=(k, d)) * 3
+    lab = rs.randint(0, k, n)
+    x = centres[lab] + rs.normal(size=(n, d)) * (0.5 + rs.rand(k)[lab, None])
+    return x, lab
+
+
+def _compare(device, dtype_np, tol):
+    import torch
+    from sklearn.mixture import GaussianMixture
+    from comemb_b200.ADSCModel.gmm_device import DeviceGaussianMixture
+    x, lab = _blobs(1500, 16, 4, 0)
+    x = x.astype(dtype_np)
+    rs = np.random.RandomState(1)
+    resp = rs.rand(1500, 4).astype(dtype_np) ** 3
+    resp /= resp.sum(1, keepdims=True)
+    sk = GaussianMixture(n_components=4, covariance_type="full", reg_covar=1e-5, tol=0.0, max_iter=5)
+    sk._initialize(x, resp)                       # sklearn's own initialisation from responsibilities
+    lowers = []
+    for _ in range(5):                            # fit_predict's loop body (sklearn/mixture/_base.py)
+        log_prob_norm, log_resp = sk._e_step(x)
+        sk._m_step(x, log_resp)
+        lowers.append(float(log_prob_norm))
+    gm = DeviceGaussianMixture(n_components=4, reg_covar=1e-5, tol=0.0, max_iter=5)
+    gm.fit(torch.as_tensor(x, device=device), resp_init=torch.as_tensor(resp, device=device))
+    assert gm.n_iter_ == 5
+    assert abs(gm.lower_bound_ - lowers[-1]) <= tol * abs(lowers[-1])
+    for got, want in ((gm.weights_, sk.weights_), (gm.means_, sk.means_), (gm.covariances_, sk.covariances_),
+                      (gm.precisions_cholesky_, sk.precisions_cholesky_)):
+        got = got.cpu().numpy()
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), np.abs(got - want).max()
+    p = gm.predict_proba(torch.as_tensor(x, device=device)).cpu().numpy()
+    assert np.abs(p - sk.predict_proba(x)).max() <= 20 * tol
+
+
+def test_device_gmm_em_steps_match_sklearn_cpu_float64():
+    _compare("cpu", np.float64, 1e-9)
+
+
+def test_device_gmm_em_steps_match_sklearn_cpu_float32():
+    # float32 (what sklearn itself computes in for float32 embeddings): five EM iterations from a deliberately diffuse
+    # start amplify fp32 summation-order differences between numpy's and torch's GEMMs to ~4e-4 relative
+    _compare("cpu", np.float32, 2e-3)
+
+
+def test_device_gmm_full_fit_recovers_blobs_cpu():
+    import torch
+    from sklearn.metrics import normalized_mutual_info_score as nmi
+    from comemb_b200.ADSCModel.gmm_device import DeviceGaussianMixture
+    x, lab = _blobs(2000, 16, 5, 3)
+    gm = DeviceGaussianMixture(n_components=5, reg_covar=1e-6, n_init=3, random_state=0).fit(torch.as_tensor(x))
+    assert gm.converged_ and nmi(lab, gm.predict(torch.as_tensor(x)).numpy()) > 0.9
+
+
+@pytest.mark.gpu
+def test_device_gmm_em_steps_match_sklearn_gpu():
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _compare("cuda", np.float64, 1e-9)
+    _compare("cuda", np.float32, 2e-3)
+
+
+@pytest.mark.gpu
+def test_community2vec_fit_device_backend_feeds_o3(golden):
+    """Community2Vec.fit(gmm_backend='device') -> centroid / inv_cov / pi on the GPU, consumed by the o3 kernel."""
+    import torch
+    from comemb_b200.ADSCModel.community_embeddings import Community2Vec
+
+    class M(object):
+        pass
+    x, lab = _blobs(600, 128, 3, 5)
+    m = M()
+    m.k = 3
+    m.node_embedding = torch.as_tensor(x.astype(np.float32), device="cuda")
+    m.vocab = {i + 1: type("V", (), {"index": i})() for i in range(600)}
+    learner = Community2Vec(m, lr=0.1, reg_covar=1e-3, gmm_backend="device")
+    learner.fit(m)
+    assert m.pi.shape == (600, 3) and m.inv_covariance_mat.shape == (3, 128, 128)
+    assert torch.allclose(m.pi.sum(1), torch.ones(600, device="cuda"), atol=1e-4)
+    before = m.node_embedding.clone()
+    learner.train(list(range(1, 601)), m, beta=0.1, iter=1)
+    assert torch.isfinite(m.node_embedding).all() and not torch.equal(before, m.node_embedding)
+    # the step pulls nodes towards their component means
+    mu = m.centroid[m.pi.argmax(1)]
+    assert ((m.node_embedding - mu).norm(dim=1) < (before - mu).norm(dim=1) + 1e-6).float().mean() > 0.95

@@ -95,6 +95,16 @@ def test_paths_to_rows_matches_prepare_sentences():
     np.random.seed(3)
     flat, off = paths_to_rows(m, big)
     assert flat.tolist() == ref[0]
+    # rectangular corpora take the vectorised path: same tokens, same np.random consumption
+    rect = np.random.RandomState(2).choice([1, 2, 3, 5, 8, 13, 77], size=(50, 6))
+    np.random.seed(4)
+    ref = [[v.index for v in p] for p in prepare_sentences(m, rect)]
+    np.random.seed(4)
+    flat, off = paths_to_rows(m, rect)
+    assert [flat[off[i]:off[i + 1]].tolist() for i in range(50)] == ref
+    np.random.seed(4)
+    flat2, off2 = paths_to_rows(m, RepeatCorpusNTimes(rect, 1))
+    assert np.array_equal(flat, flat2) and np.array_equal(off, off2)
     assert list(chunkize_serial(range(7), 3)) == [[0, 1, 2], [3, 4, 5], [6]]
     assert list(RepeatCorpusNTimes([1, 2], 2)) == [1, 2, 1, 2]
 
