@@ -8,6 +8,8 @@ Bars: ORDERED o1/o2, walks, table: BIT-EXACT (np.array_equal on fp32 tables / ui
       o3: 1e-5 relative (fp32 matmul order of the reference's BLAS is unspecified); bit-exact vs the oracle.
       HOGWILD: bit-exact vs the oracle's warp-order model when a single warp runs (no races); statistical otherwise.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -693,3 +695,60 @@ def test_sg_fused_fast_and_generic_kernels_agree_statistically(K):
     a, b = np.abs(out["fast"]).mean(), np.abs(out["generic"]).mean()
     assert a > 1e-4 and abs(a - b) / b < 0.02, (a, b)
     assert np.corrcoef(out["fast"].ravel(), out["generic"].ravel())[0, 1] > 0.95
+
+
+# ---- plumbing around the kernels -----------------------------------------------------------------------------------------------
+def test_host_o2_runner_equals_device_resident_call(K):
+    """The end-to-end path of bench.py (host tables -> pinned -> HBM -> kernel -> host) gives the same tables as the
+    device-resident call (ORDERED mode so that the comparison is exact)."""
+    c = cases.O2_CASES["o2_d128_small"]
+    node, ctx, table, walks = cases.o2_inputs(c)
+    flat, off = cases.flatten_walks(walks)
+    seeds = O.seeds_from_numpy(np.random.RandomState(2), len(walks))
+    dn, dc = dev(node), dev(ctx)
+    K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), c["lr"], c["neg"], c["W"], dev(table), mode=K.MODE_ORDERED)
+    runner = K.HostO2Runner(c["N"], c["d"], flat.size, len(walks), table)
+    hn, hc = node.copy(), ctx.copy()
+    h2d, d2h = runner.run(hn, hc, flat, off, seeds, c["lr"], c["neg"], c["W"], mode=K.MODE_ORDERED)
+    assert np.array_equal(hn, host(dn)) and np.array_equal(hc, host(dc))
+    assert h2d == 2 * node.nbytes + flat.size * 4 + (len(walks) + 1) * 8 + len(walks) * 8 and d2h == 2 * node.nbytes
+    pn, pc = runner.host_tables()  # caller-owned page-locked tables: no staging copy
+    pn[...] = node
+    pc[...] = ctx
+    runner.run(pn, pc, flat, off, seeds, c["lr"], c["neg"], c["W"], mode=K.MODE_ORDERED)
+    assert np.array_equal(pn, host(dn)) and np.array_equal(pc, host(dc))
+
+
+def test_replica_trainer_single_process_and_model_persistence(K, tmp_path):
+    import torch
+    import comemb_b200.utils.graph_utils as gu
+    from comemb_b200 import replicas
+    from comemb_b200.ADSCModel.model import Model
+    G, block = gu.sbm_graph(800, 4, 16, seed=3)
+    np.random.seed(5)
+    model = Model(G.degree(), size=128, table_size=50000, k=4)
+    model.node_embedding.mul_(0.1)
+    before = model.node_embedding.clone()
+    tr = replicas.ReplicaTrainer(model, window=5, negative=5, lr=0.025, flags=K.F_ATOMIC)
+    assert (tr.rank, tr.world) == (0, 1)
+    walks, lens = tr.step(G, 2, 30, 0.0, seed=9, pass_index=1)
+    assert walks.shape == (800, 30) and (lens == 30).all()
+    assert torch.isfinite(model.node_embedding).all() and not torch.equal(before, model.node_embedding)
+    model.save(str(tmp_path), "m")
+    back = Model.load_model(str(tmp_path), "m")
+    assert torch.equal(back.node_embedding, model.node_embedding) and torch.equal(back.table, model.table)
+    assert back.vocab_size == 800 and back.k == 4 and sorted(back.vocab) == sorted(model.vocab)
+
+
+def test_walk_files_roundtrip_like_the_reference_pipeline(K, golden, tmp_path):
+    """write_walks_to_disk -> text files -> combine_files_iter (graph_utils.py:122-163): with num_workers=1 the single
+    file holds all passes and, in ORDERED mode, exactly the reference's walks for the karate driver seed."""
+    import random
+    import comemb_b200.utils.graph_utils as gu
+    g = golden["walks"]
+    G = gu.from_csr(g["karate/ids"], g["karate/rowptr"], g["karate/col"])
+    files = gu.write_walks_to_disk(G, os.path.join(str(tmp_path), "karate.walks"), num_paths=10, path_length=20,
+                                   alpha=0, rand=random.Random(9999999999), num_workers=1)
+    assert len(files) == 1
+    got = np.array(list(gu.combine_files_iter(files)))
+    assert np.array_equal(got, golden["karate"]["walks_ids"])  # ids, as the reference's files hold them
