@@ -262,6 +262,8 @@ def run_ours(args):
         from comemb_b200.sharded import ShardedTables
         sharded = ShardedTables(n, d)
         sharded.load_rows(node_h, ctx_h)
+        if args.local_negatives:
+            table = sharded.local_negative_table(deg, CFG["table_size"])
         dist.barrier()
     rowptr, col = G.device()
     nws = CFG["walks_per_step"]
@@ -514,6 +516,8 @@ def main():
     ap.add_argument("--partition", default="replicated", choices=["replicated", "rows"],
                     help="N>1: replicated tables + NCCL averaging (default) or row-partitioned tables updated over "
                          "NVLink from inside the SGD kernel (SURVEY 8e partition B)")
+    ap.add_argument("--local-negatives", type=int, default=0,
+                    help="--partition rows: 1 = each rank samples negatives from its own row shard (less NVLink traffic)")
     ap.add_argument("--kernel", default="o2", choices=["o2", "o1", "o3", "sg"],
                     help="o2 = the judged metric; o1 / o3 = secondary kernels of the path (separate JSON line)")
     ap.add_argument("--sg-walks", type=int, default=20000)

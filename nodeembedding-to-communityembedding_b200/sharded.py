@@ -102,6 +102,19 @@ class ShardedTables(object):
                     src = torch.as_tensor(full[lo:hi]) if not hasattr(full, "is_cuda") else full[lo:hi]
                     shard[:hi - lo].copy_(src)
 
+    def local_negative_table(self, counts, table_size, power=0.75):
+        """Unigram^power table over THIS rank's rows only (values are global row ids): with shard-local negatives
+        only the node row and the positive context row of a pair can be remote, which cuts the NVLink bytes per pair
+        by about 5/7.  Changes the sampling distribution (each rank samples its own rows), so it is a
+        Hogwild-mode option for graphs that do not fit one GPU, not a parity mode.  `counts`: degrees of all rows."""
+        import torch
+        lo, hi = self.rank * self.rps, min(self.n_rows, (self.rank + 1) * self.rps)
+        w = np.asarray(counts[lo:hi], np.float64) ** power
+        cum = np.cumsum(w) / w.sum()
+        slots = (np.arange(table_size, dtype=np.float64) + 0.5) / table_size
+        rows = lo + np.searchsorted(cum, slots).clip(0, hi - lo - 1)
+        return torch.from_numpy(rows.astype(np.int32)).to(self.local_node.device)
+
     def gather(self):
         """(node, ctx) full tables on this device (for evaluation / tests)."""
         import torch
