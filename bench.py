@@ -434,7 +434,20 @@ def run_secondary(args):
             ts.append(e0.elapsed_time(e1))
         return sum(ts) / len(ts)
 
-    if args.kernel == "sg":  # the legacy fused pass (o3 gradient + SGNS per pair), Hogwild, one-hot pi
+    if args.kernel == "walks":  # the CSR walker alone (walk tokens/s; the reference's log unit is tokens, "nodes/s")
+        L = CFG["L"]
+        rowptr, col = G.device()
+        nw = 10 * n
+        walks = torch.empty((nw, L), dtype=torch.int32, device="cuda")
+        lens = torch.empty(nw, dtype=torch.int32, device="cuda")
+        lib = _lib.load()
+        ms = timed(lambda: _lib.check(lib.comemb_walks_csr(rowptr.data_ptr(), col.data_ptr(), n, 10, L, 0.0, 5,
+                                                           K.MODE_HOGWILD, 0, nw, walks.data_ptr(), lens.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream)))
+        v = nw * L / (ms * 1e-3)
+        out.update({"metric": "walk_tokens_per_sec", "value": v, "unit": "tokens/s", "ms_per_step": ms, "walks": nw,
+                    "roofline": {"bound": "latency (dependent rowptr->col loads)", "written_gbs": v * 4 / 1e9}})
+    elif args.kernel == "sg":  # the legacy fused pass (o3 gradient + SGNS per pair), Hogwild, one-hot pi
         from comemb_b200.utils import graph_utils as gu
         L, W, Kc = CFG["L"], CFG["W"], CFG.get("blocks", 50)
         deg = np.ascontiguousarray(np.diff(G.rowptr), np.float64)
@@ -518,7 +531,7 @@ def main():
                          "NVLink from inside the SGD kernel (SURVEY 8e partition B)")
     ap.add_argument("--local-negatives", type=int, default=0,
                     help="--partition rows: 1 = each rank samples negatives from its own row shard (less NVLink traffic)")
-    ap.add_argument("--kernel", default="o2", choices=["o2", "o1", "o3", "sg"],
+    ap.add_argument("--kernel", default="o2", choices=["o2", "o1", "o3", "sg", "walks"],
                     help="o2 = the judged metric; o1 / o3 = secondary kernels of the path (separate JSON line)")
     ap.add_argument("--sg-walks", type=int, default=20000)
     ap.add_argument("--sg-shrink", type=int, default=0, help="1: random window shrinking like the legacy train_sg")

@@ -98,17 +98,6 @@ def _const_dev(arr, dtype):
     return hit
 
 
-def _u32_dev(a):
-    """numpy uint32/int array or torch tensor -> device tensor holding uint32 bit patterns (stored as int32)."""
-    torch = _torch()
-    if isinstance(a, torch.Tensor):
-        if a.dtype in (torch.int32, torch.uint32):
-            return a.contiguous() if a.is_cuda else a.contiguous().cuda()
-        return a.to(torch.int64).to(torch.int32).cuda() if False else a.to(device="cuda", dtype=torch.int32)
-    a = np.ascontiguousarray(a, dtype=np.uint32)
-    return torch.from_numpy(a.view(np.int32)).cuda()
-
-
 def _dev(a, np_dtype):
     torch = _torch()
     if a is None:

@@ -752,3 +752,68 @@ def test_walk_files_roundtrip_like_the_reference_pipeline(K, golden, tmp_path):
     assert len(files) == 1
     got = np.array(list(gu.combine_files_iter(files)))
     assert np.array_equal(got, golden["karate"]["walks_ids"])  # ids, as the reference's files hold them
+
+
+def test_full_size_properties_o1_o3_walks_config2_shape(K):
+    """BASELINE config-2 sizes for the other kernels of the path, through size-independent properties.
+    o1 (2M edges): lr=0 leaves the table bit-identical; a real step moves only rows that are edge endpoints and
+    keeps everything finite.  o3 (100K rows, K=50): rows with pi == 0 are untouched, beta=0 is the identity, and one
+    step contracts every other row towards its community mean when inv_cov = I.  Walks (100K-node SBM): every node
+    starts exactly one walk per pass, every step follows an edge, all walks have full length."""
+    import torch
+    import comemb_b200.utils.graph_utils as gu
+    n, d = 100000, 128
+    G, block = gu.sbm_graph(n, 50, 40, seed=12345)
+    rowptr, col = G.rowptr, G.col
+    g = torch.Generator(device="cuda").manual_seed(3)
+    node = (torch.rand((n, d), device="cuda", generator=g) * 2 - 1) * 0.05
+    table = dev(O.make_table(np.diff(rowptr).astype(np.float64), 5000000))
+    src = np.repeat(np.arange(n, dtype=np.int64), np.diff(rowptr))
+    keep = src < col
+    keep &= (np.arange(keep.size) % 50 != 0) | (src < n // 2)  # leave some structure; all rows still touched or not
+    edges_h = np.stack([src[keep], col[keep].astype(np.int64)], 1).astype(np.int32)
+    edges_h = edges_h[edges_h[:, 0] >= 1000]  # rows 1..999 can still be drawn as negatives (read-only in o1)
+    edges_h = edges_h[edges_h[:, 1] >= 1000]
+    edges = torch.from_numpy(edges_h).cuda()
+    n0 = node.clone()
+    K.o1_batch(node, edges, None, 0.0, 5, table, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC, base_seed=1)
+    assert torch.equal(node, n0)
+    K.o1_batch(node, edges, None, 0.025, 5, table, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC, base_seed=1,
+               edge_stride=1234567)
+    assert torch.isfinite(node).all()
+    moved = (node != n0).any(1)
+    endpoint = torch.zeros(n, dtype=torch.bool, device="cuda")
+    endpoint[edges.reshape(-1).long()] = True
+    assert not (moved & ~endpoint).any() and moved.sum() > 0.99 * endpoint.sum()
+    assert torch.equal(node[:1000], n0[:1000])  # never an endpoint here: targets are read-only in o1 (pyx:245)
+
+    # o3
+    Kc = 50
+    mu = (torch.rand((Kc, d), device="cuda", generator=g) - 0.5)
+    inv = torch.eye(d, device="cuda").repeat(Kc, 1, 1).contiguous()
+    pi = torch.zeros((n, Kc), device="cuda")
+    comm = torch.from_numpy((block % Kc).astype(np.int64)).cuda()
+    pi[torch.arange(n, device="cuda"), comm] = 1.0
+    pi[::7] = 0.0
+    x0 = node.clone()
+    inv_t = K.transpose_blocks(inv)
+    K.o3_batch(node, None, mu, inv_t, pi, 0.0, 0.1, iters=1)
+    assert torch.equal(node, x0)  # beta = 0: gradient scale 0
+    K.o3_batch(node, None, mu, inv_t, pi, float(Kc), 0.1, iters=1)  # beta/K = 1: x -= 0.1*clip(x - mu_c, +-5)
+    assert torch.equal(node[::7], x0[::7])
+    want = x0 - 0.1 * (x0 - mu[comm]).clamp(-5, 5)
+    live = torch.ones(n, dtype=torch.bool, device="cuda")
+    live[::7] = False
+    assert (node[live] - want[live]).abs().max() < 1e-6
+
+    # walks
+    walks, lens = gu.build_deepwalk_corpus(G, 2, 80, alpha=0.0, seed=11, mode=gu.MODE_HOGWILD, return_device=True)
+    assert walks.shape == (2 * n, 80) and bool((lens == 80).all())
+    for p in range(2):
+        starts = walks[p * n:(p + 1) * n, 0].long()
+        assert torch.equal(torch.sort(starts).values, torch.arange(n, device="cuda"))
+    a, b = walks[:, :-1].reshape(-1).long().cpu().numpy(), walks[:, 1:].reshape(-1).long().cpu().numpy()
+    sel = np.random.RandomState(0).choice(a.size, 200000, replace=False)
+    key = np.sort(src * n + col.astype(np.int64))
+    q = a[sel] * n + b[sel]
+    assert (key[np.searchsorted(key, q).clip(0, key.size - 1)] == q).all()  # every sampled step is an edge
