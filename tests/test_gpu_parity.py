@@ -817,3 +817,89 @@ def test_full_size_properties_o1_o3_walks_config2_shape(K):
     key = np.sort(src * n + col.astype(np.int64))
     q = a[sel] * n + b[sel]
     assert (key[np.searchsorted(key, q).clip(0, key.size - 1)] == q).all()  # every sampled step is an edge
+
+
+def test_row_offsets_beyond_2_to_32_elements(K):
+    """Maximum sizes: tables of 34M rows x 128 = 4.35e9 elements (> 2^32; the reference computes `uint32 row * int size`
+    and wraps there, pyx:120).  The same walks/negatives are run on a compact 300-row table and on the huge table with
+    the rows placed at its far end; ORDERED mode, so the touched rows must agree bit for bit, and nothing else moves."""
+    import torch
+    N_big, n_small, d = 34_000_000, 300, 128
+    free, _ = torch.cuda.mem_get_info()
+    if free < 2 * N_big * d * 4 + (8 << 30):
+        pytest.skip("needs ~36 GB of free HBM")
+    rs = np.random.RandomState(0)
+    node_s = (rs.uniform(-1, 1, (n_small, d)) * 0.3).astype(np.float32)
+    ctx_s = (rs.uniform(-1, 1, (n_small, d)) * 0.3).astype(np.float32)
+    base = N_big - n_small - 5  # compact row r <-> big row base + r  (offsets > 2^32 elements)
+    assert (base * d) > 2 ** 32
+    table_s = np.sort(rs.randint(1, n_small, 4000)).astype(np.uint32)
+    walks_s = rs.randint(0, n_small, (4, 30)).astype(np.uint32)
+    off = (np.arange(5) * 30).astype(np.int64)
+    seeds = O.seeds_from_numpy(rs, 4)
+    a, b = dev(node_s), dev(ctx_s)
+    off1 = dev(np.array([0, 30], np.int64))
+
+    def run(node_t, ctx_t, walks2d, table_t):
+        # ORDERED over all walks, then HOGWILD one walk per launch (a single warp: deterministic)
+        K.o2_batch(node_t, ctx_t, dev(walks2d.reshape(-1)), dev(off), dev(seeds), 0.025, 5, 5, table_t,
+                   mode=K.MODE_ORDERED)
+        for i in range(walks2d.shape[0]):
+            K.o2_batch(node_t, ctx_t, dev(walks2d[i]), off1, dev(seeds[i:i + 1]), 0.025, 5, 5, table_t,
+                       mode=K.MODE_HOGWILD)
+
+    run(a, b, walks_s, dev(table_s))
+    big_n = torch.zeros((N_big, d), dtype=torch.float32, device="cuda")
+    big_c = torch.zeros((N_big, d), dtype=torch.float32, device="cuda")
+    big_n[base:base + n_small] = dev(node_s)
+    big_c[base:base + n_small] = dev(ctx_s)
+    tb = dev((table_s.astype(np.int64) + base).astype(np.uint32))
+    run(big_n, big_c, (walks_s.astype(np.int64) + base).astype(np.uint32), tb)
+    assert torch.equal(big_n[base:base + n_small], a) and torch.equal(big_c[base:base + n_small], b)
+    assert not bool(big_n[:base].any()) and not bool(big_c[:base].any())  # nothing wrapped around into low rows
+    assert not torch.equal(a, dev(node_s))
+
+
+def test_config3_blogcatalog_shape_full_training(K):
+    """BASELINE configs[2]: a 10K-node / ~330K-edge graph with 39 communities, d=128, conf.ini hyper-parameters
+    (negative=3, 5 walks of length 80, window 5, lambda1=1, lambda2=0.1, 2 iterations), full o1 + o2 + GMM + o3 in
+    the HEAD order and then the fused (legacy train_sg) form, Hogwild mode.  Properties: everything stays finite, the
+    tables stay finite, the GMM recovers the planted communities, the fused pass keeps that structure."""
+    import torch
+    import comemb_b200.utils.graph_utils as gu
+    from comemb_b200.ADSCModel.model import Model
+    from comemb_b200.ADSCModel.node_embeddings import Node2Vec
+    from comemb_b200.ADSCModel.context_embeddings import Context2Vec
+    from comemb_b200.ADSCModel.community_embeddings import Community2Vec
+    from sklearn.metrics import normalized_mutual_info_score as nmi
+    n, k, d = 10140, 39, 128
+    G, block = gu.sbm_graph(n, k, 66, p_in=0.7, seed=7)
+    assert 300000 < G.number_of_edges() < 360000
+    np.random.seed(3)
+    model = Model(G.degree(), size=d, table_size=1000000, k=k)
+    model.node_embedding.mul_(0.05)
+    n2v = Node2Vec(workers=16, negative=3, lr=0.025)
+    c2v = Context2Vec(window_size=5, workers=16, negative=3, lr=0.025)
+    com = Community2Vec(model, lr=0.025, reg_covar=1e-4, gmm_backend="device")
+    walks, lens = gu.build_deepwalk_corpus(G, 5, 80, alpha=0, seed=1, mode=gu.MODE_HOGWILD, return_device=True)
+    off = torch.arange(walks.shape[0] + 1, dtype=torch.int64, device="cuda") * 80
+    loss0 = K.o2_pos_loss(model.node_embedding, model.context_embedding, walks.reshape(-1), off, 5)
+    for it in range(2):
+        n2v.train(model, edges=G.edges(), iter=1)
+        c2v.train(model, paths=(walks, lens), total_nodes=walks.numel(), alpha=1.0)
+        com.fit(model)
+        com.train(G.nodes(), model, beta=0.1, iter=5)
+    loss1 = K.o2_pos_loss(model.node_embedding, model.context_embedding, walks.reshape(-1), off, 5)
+    assert torch.isfinite(model.node_embedding).all() and torch.isfinite(model.context_embedding).all()
+    # (the positive-pair term alone is not monotone early in SGNS training -- it starts at log 2 with a zero context
+    # table and first rises while the negatives push rows apart -- so it is only required to stay finite and bounded)
+    assert loss0[1] == loss1[1] and np.isfinite(loss1[0]) and loss1[0] / loss1[1] < 6.0
+    q_head = nmi(block, model.pi.argmax(1).cpu().numpy())
+    assert q_head > 0.8, q_head
+    # the fused form on the same state: o3 + SGNS per pair (pi from the GMM: one-hot rows -> tensor-core kernel)
+    K.sg_batch(model.node_embedding, model.context_embedding, walks.reshape(-1), off, None, None, 0.025, 3, 5,
+               model.table, model.centroid, model.inv_covariance_mat.contiguous(), model.pi.contiguous(), 1.0, 0.1, 0,
+               mode=K.MODE_HOGWILD, flags=K.F_ATOMIC, base_seed=5)
+    assert torch.isfinite(model.node_embedding).all()
+    com.fit(model)
+    assert nmi(block, model.pi.argmax(1).cpu().numpy()) > q_head - 0.1
