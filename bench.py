@@ -100,7 +100,7 @@ def physical_gpu_index(local):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(node, ctx, table, walks, W, neg, lr, threads, seconds_budget=None):
+def cpu_reference_run(node, ctx, table, walks, W, neg, lr, threads):
     """Time the reference's compiled train_o2 (oracle/_ref, `tuned` build) over `walks` (list of uint32 arrays) with
     `threads` Python threads, the reference's own Hogwild scheme (context_embeddings.py:72-98).  Falls back to the
     oracle port (C restatement, ctypes releases the GIL) when oracle/_ref is absent.  Returns (pairs/s, kind, info)."""

@@ -307,8 +307,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_kernel(
 //     walk's state by NEG steps with one multiply-add;  the NEXT pair's table lookups are issued one pair ahead;
 //   * all NEG+1 rows are loaded unconditionally (a dropped sample just gets g = 0), no per-row predicate moves;
 //   * one transposed reduction + one lane-parallel sigma evaluation per pair;
-//   * duplicate samples inside a pair (which must see each other's update, pyx:146-147) are detected with one
-//     match.any and handled by a sequential path that re-reads rows from memory.
+//   * duplicate samples inside a pair (which must see each other's update, pyx:146-147) are detected with plain
+//     warp-uniform compares (match.any kept the ADU pipe 53 % busy) and handled by a sequential path that re-reads
+//     rows from memory;
+//   * SHARDED: row r lives in shard r / rows_per_shard (possibly a peer GPU's memory, see sharded.py).
 template <bool ATOMIC, int NEG, int MINB, bool HINT, bool SHARDED>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_kernel(const O2Params P) {
     static_assert(NEG >= 1 && NEG <= 7, "positive + negatives must fit the 8 reduction slots");
