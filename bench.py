@@ -181,8 +181,8 @@ def run_reference(args):
     table = O.make_table(deg, CFG["table_size"])
     node, ctx = init_tables_host(CFG["n"], CFG["d"])
     threads = os.cpu_count() or 1
-    # bounded sample per step: ~4 s of CPU work per step at ~3e5 pairs/s/thread
-    walks_per_step = max(threads, min(CFG["n"], int(threads * 3e5 * 4 / pairs_of_len(CFG["L"], CFG["W"]))))
+    # bounded sample per step: ~3 s of CPU work per step at ~1.2e6 pairs/s/core
+    walks_per_step = max(threads, min(CFG["n"], int(threads * 1.2e6 * 3 / pairs_of_len(CFG["L"], CFG["W"]))))
     all_walks = host_walks(G, walks_per_step * (args.steps + args.warmup), CFG["L"], 7)
     times, pairs, kind = [], 0, None
     for s in range(args.warmup + args.steps):
@@ -384,7 +384,7 @@ def run_ours(args):
         try:
             from oracle import oracle as O
             threads = os.cpu_count() or 1
-            nw = max(threads, int(threads * 3e5 * 12 / pairs_of_len(L, W)))  # ~12 s of CPU work
+            nw = max(threads, int(threads * 1.2e6 * 12 / pairs_of_len(L, W)))  # ~10 s of CPU work at ~1.2e6 pairs/s/core
             nw = min(nw, nws)
             wnp = walks.cpu().numpy().view(np.uint32)
             ln = lens.cpu().numpy()
