@@ -55,6 +55,7 @@ class Context2Vec(object):
             n_walks = off_h.size - 1
             walks = torch.from_numpy(flat.view(np.int32)).to(dev)
             off = torch.from_numpy(off_h).to(dev)
+        K.check_row_tokens(walks, model.vocab_size)
         seeds = torch.from_numpy(K.draw_seeds(n_walks).view(np.int64)).to(dev)  # pyx:477, path order
         flags = 0
         alias = None

@@ -58,6 +58,7 @@ class Node2Vec(object):
         mode = self._mode()
         dev = model.node_embedding.device
         e = torch.from_numpy(flat.view(np.int32)).to(dev)
+        K.check_row_tokens(e, model.vocab_size, "edge endpoints")
         flags = 0
         if mode == K.MODE_ORDERED:
             seeds = torch.from_numpy(K.draw_seeds(n_edges).view(np.int64)).to(dev)  # pyx:427, edge order

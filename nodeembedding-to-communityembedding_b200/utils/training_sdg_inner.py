@@ -127,6 +127,20 @@ def _indices(py_items):
 
 
 # ---- batch entry points -------------------------------------------------------------------------------------------------
+def check_row_tokens(tokens, n_rows, what="walk tokens"):
+    """Raise if a uint32 row token (other than TOKEN_NONE) addresses a row >= n_rows.  The kernels, like the
+    reference (pyx:410-411), do not bounds-check; the learners call this once per corpus so that a bad id becomes a
+    Python error instead of an illegal device access."""
+    torch = _torch()
+    if tokens is None or tokens.numel() == 0:
+        return
+    t = tokens.reshape(-1)
+    t64 = t.to(torch.int64) & 0xFFFFFFFF  # stored as int32 bit patterns
+    bad = (t64 >= int(n_rows)) & (t64 != TOKEN_NONE)
+    if bool(bad.any()):
+        raise ComembError("%s: row index %d out of range for a table of %d rows" % (what, int(t64[bad][0]), n_rows))
+
+
 def hogwild_concurrency(n_rows, workers=1):
     """Cap on concurrently processed walks/edges in HOGWILD mode: the reference's `workers`, or as many as keep the
     expected number of in-flight updates per table row below ~1/4 (7 rows per pair -> n_rows/28), whichever is larger.

@@ -133,6 +133,9 @@ def test_per_call_train_o1_numpy_in_place(K, golden):
 
 def test_error_behaviour(K):
     import torch
+    with pytest.raises(K.ComembError):  # a CSR-row token beyond the table: caught by the learner-level check
+        K.check_row_tokens(dev(np.array([0, 5, 99, cases.TOKEN_NONE], np.uint32)), 50)
+    K.check_row_tokens(dev(np.array([0, 49, cases.TOKEN_NONE], np.uint32)), 50)
     node = np.zeros((4, 8), np.float64)
     with pytest.raises(K.ComembError):
         K.train_o2(node, node, [O.RefVocab(0)], 0.1, 1, 1, np.ones(4, np.uint32), py_size=8)
