@@ -100,12 +100,12 @@ def physical_gpu_index(local):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(node, ctx, table, walks, W, neg, lr, threads):
+def cpu_reference_run(node, ctx, table, walks, W, neg, lr, threads, variant="tuned"):
     """Time the reference's compiled train_o2 (oracle/_ref, `tuned` build) over `walks` (list of uint32 arrays) with
     `threads` Python threads, the reference's own Hogwild scheme (context_embeddings.py:72-98).  Falls back to the
     oracle port (C restatement, ctypes releases the GIL) when oracle/_ref is absent.  Returns (pairs/s, kind, info)."""
     from oracle import oracle as O
-    kind = "reference" if O.ref_available("tuned") else "port"
+    kind = "reference" if O.ref_available(variant) else "port"
     d = node.shape[1]
     total_pairs = sum(pairs_of_len(len(w), W) for w in walks)
     shards = [walks[t::threads] for t in range(threads)]
@@ -116,7 +116,7 @@ def cpu_reference_run(node, ctx, table, walks, W, neg, lr, threads):
             limiter = threadpool_limits(limits=1, user_api="blas")
         except Exception:
             limiter = None
-        ref = O.load_ref("tuned")
+        ref = O.load_ref(variant)
         vocab = [O.RefVocab(i) for i in range(node.shape[0])]
         paths = [[[vocab[t] for t in w.tolist()] for w in sh] for sh in shards]  # pre-built Vocab lists (untimed)
 
@@ -391,7 +391,17 @@ def run_ours(args):
             ws = [wnp[i, :ln[i]].copy() for i in range(nw)]
             tab_h = table.cpu().numpy().view(np.uint32)
             v, kind, info = cpu_reference_run(node.cpu().numpy(), ctx.cpu().numpy(), tab_h, ws, W, neg, lr, threads)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+            extra = {}
+            try:  # also: 1 thread of the tuned build, and the stock build (cython_utils.py flags) on 1 thread
+                v1, _, _ = cpu_reference_run(node.cpu().numpy(), ctx.cpu().numpy(), tab_h, ws[:1500], W, neg, lr, 1)
+                extra["one_thread_value"] = v1
+                if O.ref_available("stock"):
+                    vs, _, _ = cpu_reference_run(node.cpu().numpy(), ctx.cpu().numpy(), tab_h, ws[:800], W, neg, lr, 1,
+                                                 variant="stock")
+                    extra["stock_build_one_thread_value"] = vs
+            except Exception as e:
+                extra["extra_error"] = repr(e)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, **extra,
                                     "sample": "%d walks (%d pair updates) of the same workload, %.1f s, %s" % (
                                         info["walks"], info["pairs"], info["seconds"],
                                         "reference Cython train_o2, tuned build, one Python thread per core"
@@ -494,6 +504,30 @@ def run_secondary(args):
         ms = timed(lambda: K.o1_batch(node, edges, None, 0.025, neg, table, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC,
                                       base_seed=3, edge_stride=stride))
         v = 2 * E / (ms * 1e-3)
+        try:  # the reference's train_o1 (pyx:407) on the host cores, bounded sample of the same edge list
+            from oracle import oracle as O
+            if O.ref_available("tuned"):
+                ref = O.load_ref("tuned")
+                threads = os.cpu_count() or 1
+                ne = min(E, 40000 * threads)
+                host_node, host_tab = node.cpu().numpy(), table.cpu().numpy().view(np.uint32)
+                vocab = [O.RefVocab(i) for i in range(n)]
+                eh = edges[:ne].cpu().numpy()
+                shards = [[[vocab[a], vocab[b]] for a, b in eh[t::threads].tolist()] for t in range(threads)]
+
+                def work(t):
+                    buf = np.zeros(d, np.float32)
+                    for e in shards[t]:
+                        ref.train_o1(host_node, e, 0.025, neg, host_tab, py_size=d, py_work=buf)
+                ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+                t0 = time.perf_counter()
+                [th.start() for th in ths]
+                [th.join() for th in ths]
+                dt = time.perf_counter() - t0
+                out["cpu_baseline"] = {"value": 2 * ne / dt, "unit": "directed-updates/s", "cores": threads,
+                                       "kind": "reference", "sample": "%d edges, %.1f s, train_o1 tuned build" % (ne, dt)}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "kind": "reference", "sample": "failed: %r" % (e,)}
         out.update({"metric": "o1_directed_updates_per_sec", "value": v, "unit": "directed-updates/s", "ms_per_step": ms,
                     "edges": E, "roofline": {"bound": "hbm", "achieved": v * 4096 / 1e9, "peak": peak, "unit": "GB/s",
                                              "frac": v * 4096 / 1e9 / peak, "algorithmic_bytes_per_update": 4096}})
@@ -509,6 +543,19 @@ def run_secondary(args):
         inv_t = K.transpose_blocks(inv)
         ms = timed(lambda: K.o3_batch(node, None, mu, inv_t, pi, 0.1, 0.025, iters=1))
         v = n / (ms * 1e-3)
+        try:  # the reference's o3 is numpy code that cannot travel; the oracle's C port on one host core instead
+            from oracle import oracle as O
+            ns = 4000
+            xs = node[:ns].cpu().numpy().copy()
+            t0 = time.perf_counter()
+            O.o3_batch(xs, np.arange(ns, dtype=np.uint32), mu.cpu().numpy(), inv.cpu().numpy(), pi_h[:ns].copy(), 0.1,
+                       0.025, 1)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": ns / dt, "unit": "node-updates/s", "cores": 1, "kind": "port",
+                                   "sample": "%d rows, dense loop over K=%d communities (no sparsity skip), %.1f s" % (
+                                       ns, Kc, dt)}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "kind": "port", "sample": "failed: %r" % (e,)}
         out.update({"metric": "o3_node_updates_per_sec", "value": v, "unit": "node-updates/s", "ms_per_step": ms,
                     "K": Kc, "pi": "one-hot", "flop_per_node": 2 * d * d,
                     "roofline": {"bound": "l2/fp64-fma", "achieved_gflops": v * 2 * d * d / 1e9,
