@@ -282,10 +282,18 @@ def test_o2_hogwild_generic_kernel_at_d128(K, name):
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
 
 
+@pytest.mark.parametrize("neg,d", [(1, 128), (2, 128), (7, 128), (12, 64), (3, 128), (4, 128)])
+def test_o2_hogwild_other_negative_counts(K, neg, d):
+    """negative = 3..5 at size 128 take the specialised kernel (compile-time NEG); everything else the generic kernel,
+    which gathers negatives in batches of 5 (7 and 12: several batches).  Single warp vs the oracle, bit for bit."""
+    c = dict(cases.O2_CASES["o2_d128_small"], neg=neg, d=d, seed=900 + neg)
+    _o2_single_warp(K, c, False)
+
+
 def _o2_single_warp(K, name, atomic):
     """With one walk per launch nothing races: the Hogwild kernel must equal the sequential oracle evaluated with
     the kernel's own summation order, bit for bit (plain stores) / to rounding (red.add adds deltas in L2)."""
-    c = cases.O2_CASES[name]
+    c = name if isinstance(name, dict) else cases.O2_CASES[name]
     node, ctx, table, walks = cases.o2_inputs(c)
     seeds = O.seeds_from_numpy(np.random.RandomState(3), len(walks))
     dn, dc, dt = dev(node), dev(ctx), dev(table)
