@@ -619,6 +619,101 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) o1_hogwild_kernel(const 
     }
 }
 
+// ---- o1, headline shape: size == 128, NEG known at compile time -------------------------------------------------------------
+// Same result as o1_hogwild_kernel with the o2 d=128 instruction diet: the 2*NEG samples of an edge are fetched with one
+// load (lane k jumps straight to LCG state k), each directed update reduces its NEG+1 dots with one transposed 8-slot
+// reduction and evaluates sigma once per lane; targets are read-only in o1 (pyx:245), so there is no duplicate path.
+template <bool ATOMIC, int NEG>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3) o1_hogwild_d128_kernel(const O1Params P) {
+    static_assert(NEG >= 1 && NEG <= 7, "positive + negatives must fit the 8 reduction slots");
+    constexpr int D = 128;
+    constexpr LcgJump<2 * NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const float lr = P.lr;
+    float *const node_l = P.node + 4 * lane;
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    const int pi = ((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1);
+    const float my_label = pi == 0 ? 1.f : 0.f;
+    const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+
+    // one directed update (fast_o1): row x against `target` (label 1) and samples tt[0..NEG) (label 0); returns work
+    auto directed = [&](const float4 &x, const float4 &target, uint32_t word_index, const uint32_t (&tt)[NEG],
+                        const float4 (&c)[NEG]) -> float4 {
+        float p[8];
+        p[0] = fmaf(x.w, target.w, fmaf(x.z, target.z, fmaf(x.y, target.y, fmaf(x.x, target.x, 0.f))));
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+            p[k + 1] = k < NEG ? fmaf(x.w, c[k < NEG ? k : 0].w,
+                                      fmaf(x.z, c[k < NEG ? k : 0].z,
+                                           fmaf(x.y, c[k < NEG ? k : 0].y, fmaf(x.x, c[k < NEG ? k : 0].x, 0.f))))
+                               : 0.f;
+        const float fm = reduce8_transposed(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], lane);
+        bool live = pi == 0;
+#pragma unroll
+        for (int k = 0; k < NEG; k++) live = live || (pi == k + 1 && tt[k] != word_index);  // pyx:234-235
+        float gm = 0.f;
+        if (live && fm > -MAX_EXP_F && fm < MAX_EXP_F) gm = __fmul_rn(my_label - lut[lut_index(fm)], lr);  // pyx:243
+        float4 work = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            const float g = __shfl_sync(FULL, gm, lane_of_p(0));
+            work.x = fmaf(g, target.x, work.x); work.y = fmaf(g, target.y, work.y);
+            work.z = fmaf(g, target.z, work.z); work.w = fmaf(g, target.w, work.w);
+        }
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            const float g = __shfl_sync(FULL, gm, lane_of_p(k + 1));
+            work.x = fmaf(g, c[k].x, work.x); work.y = fmaf(g, c[k].y, work.y);  // pyx:245
+            work.z = fmaf(g, c[k].z, work.z); work.w = fmaf(g, c[k].w, work.w);
+        }
+        return work;
+    };
+
+    for (int64_t u = warp0; u < P.n_edges; u += n_warps) {
+        const int64_t q = P.stride > 1 ? (int64_t)(((uint64_t)u * (uint64_t)P.stride) % (uint64_t)P.n_edges) : u;
+        const uint32_t e0 = __ldg(P.edges + 2 * q), e1 = __ldg(P.edges + 2 * q + 1);
+        const uint64_t rnd = P.seeds ? P.seeds[q] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)q)) & LCG_MASK);
+        // all 2*NEG samples of the edge with one load: lane k draws sample k (pyx:232-233, one stream per edge)
+        const uint32_t tmine = (lane < 2 * NEG) ? draw_fetch(P.draw, (myA * rnd + myC) & LCG_MASK) : 0u;
+        float *p0 = node_l + (int64_t)e0 * D, *p1 = node_l + (int64_t)e1 * D;
+        float4 r0 = __ldcg(reinterpret_cast<const float4 *>(p0));
+        float4 r1 = (e1 == e0) ? r0 : __ldcg(reinterpret_cast<const float4 *>(p1));
+        uint32_t ta[NEG], tb[NEG];
+        float4 ca[NEG], cb[NEG];
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            ta[k] = __shfl_sync(FULL, tmine, k);
+            tb[k] = __shfl_sync(FULL, tmine, NEG + k);
+            ca[k] = __ldcg(reinterpret_cast<const float4 *>(node_l + (int64_t)ta[k] * D));
+            cb[k] = __ldcg(reinterpret_cast<const float4 *>(node_l + (int64_t)tb[k] * D));
+        }
+        // pyx:444: row e0 against target e1
+        float4 work = directed(r0, r1, e1, ta, ca);
+        if (ATOMIC) red_add4(p0, work);
+        r0 = make_float4(r0.x + work.x, r0.y + work.y, r0.z + work.z, r0.w + work.w);
+        if (!ATOMIC) st4(p0, r0);
+        if (e1 == e0) r1 = r0;
+        // pyx:447: row e1 against the UPDATED row e0; samples equal to e0 must see that update too
+#pragma unroll
+        for (int k = 0; k < NEG; k++)
+            if (tb[k] == e0) cb[k] = r0;
+        work = directed(r1, r0, e0, tb, cb);
+        if (ATOMIC)
+            red_add4(p1, work);
+        else
+            st4(p1, make_float4(r1.x + work.x, r1.y + work.y, r1.z + work.z, r1.w + work.w));
+    }
+}
+
 template <typename K>
 int grid_for(K kernel, int64_t n_units, size_t dyn_smem = 0) {
     int dev = 0, sms = 0, per_sm = 0;
@@ -742,6 +837,23 @@ int launch_o1_hogwild(float *node, int size, const uint32_t *edges, int64_t n_ed
     P.negative = negative; P.lr = lr; P.stride = stride > 1 ? stride % n_edges : 0;
     P.glut = comemb_lut_device();
     const bool vec = (size % 4) == 0;
+    if (size == 128 && g_tuning.variant != 9) {
+#define COMEMB_O1(N)                                                                  \
+    case N:                                                                           \
+        if (atomic) {                                                                 \
+            auto k = o1_hogwild_d128_kernel<true, N>;                                 \
+            k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);            \
+        } else {                                                                      \
+            auto k = o1_hogwild_d128_kernel<false, N>;                                \
+            k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);            \
+        }                                                                             \
+        return (int)cudaGetLastError();
+        switch (negative) {
+            COMEMB_O1(3) COMEMB_O1(4) COMEMB_O1(5)
+            default: break;
+        }
+#undef COMEMB_O1
+    }
     if (size <= 128) return vec ? launch_o1_t<1, true>(P, atomic, st) : launch_o1_t<1, false>(P, atomic, st);
     if (size <= 256) return vec ? launch_o1_t<2, true>(P, atomic, st) : launch_o1_t<2, false>(P, atomic, st);
     return vec ? launch_o1_t<4, true>(P, atomic, st) : launch_o1_t<4, false>(P, atomic, st);
