@@ -12,6 +12,8 @@
 // This is a correctness mode: a single warp, no parallelism across pairs (pair p+1 must see every write of pair p).
 #include "comemb_common.cuh"
 
+bool g_force_generic_ordered = false;  // tests: comemb_set_tuning(.., .., 900) routes size 128 to the generic kernels
+
 namespace {
 
 // ---- dot product in the reference's summation order ---------------------------------------------------------------------
@@ -309,6 +311,68 @@ __global__ void __launch_bounds__(32)
     if (n_tokens && lane == 0) *n_tokens += tokens;
 }
 
+// ---- o1 ORDERED, size == 128, register-resident (same arithmetic as pair_o1 / dot_refblas, see o2_ordered_d128_kernel) -
+template <int NEG>
+__global__ void __launch_bounds__(32)
+    o1_ordered_d128_kernel(float *node, const uint32_t *edges, int64_t n_edges, const uint64_t *seeds,
+                           uint64_t base_seed, Sampler S, float lr, bool quirk, const float *g_exp_table) {
+    constexpr int D = 128;
+    constexpr LcgJump<2 * NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
+    __syncwarp();
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    // one directed update (fast_o1, pyx:205-249): returns row x + work
+    auto directed = [&](const Row4 &x, const Row4 &target, uint32_t word_index, const uint32_t (&tt)[NEG],
+                        const Row4 (&c)[NEG]) -> Row4 {
+        Row4 work = {0.f, 0.f, 0.f, 0.f};
+        {
+            const float f = dot128_refblas(x, target, quirk);
+            if (f > -MAX_EXP_F && f < MAX_EXP_F) fma_row4(work, __fmul_rn(1.f - lut[lut_index(f)], lr), target);
+        }
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            if (tt[k] == word_index) continue;  // pyx:234-235
+            const float f = dot128_refblas(x, c[k], quirk);
+            if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
+            fma_row4(work, __fmul_rn(0.f - lut[lut_index(f)], lr), c[k]);  // pyx:243-245
+        }
+        Row4 nx = {x.v0 + work.v0, x.v1 + work.v1, x.v2 + work.v2, x.v3 + work.v3};  // pyx:247
+        return nx;
+    };
+    for (int64_t q = 0; q < n_edges; q++) {  // node_embeddings.py:70-71
+        const uint32_t e0 = edges[2 * q], e1 = edges[2 * q + 1];
+        const uint64_t rnd = seeds ? seeds[q] : (splitmix64(base_seed ^ splitmix64((uint64_t)q)) & LCG_MASK);
+        const uint32_t tmine = (lane < 2 * NEG) ? S.table[table_slot((myA * rnd + myC) & LCG_MASK, S.mod)] : 0u;
+        Row4 r0 = ld_row4(node + (int64_t)e0 * D, lane);
+        Row4 r1 = ld_row4(node + (int64_t)e1 * D, lane);
+        uint32_t ta[NEG], tb[NEG];
+        Row4 ca[NEG], cb[NEG];
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            ta[k] = __shfl_sync(FULL, tmine, k);
+            tb[k] = __shfl_sync(FULL, tmine, NEG + k);
+            ca[k] = ld_row4(node + (int64_t)ta[k] * D, lane);
+            cb[k] = ld_row4(node + (int64_t)tb[k] * D, lane);
+        }
+        r0 = directed(r0, r1, e1, ta, ca);  // pyx:444 (targets are read-only: a sample equal to e0 is the old row)
+        st_row4(node + (int64_t)e0 * D, lane, r0);
+        if (e1 == e0) r1 = r0;
+#pragma unroll
+        for (int k = 0; k < NEG; k++)
+            if (tb[k] == e0) cb[k] = r0;  // pyx:447 sees the updated row e0, also as a sample
+        r1 = directed(r1, r0, e0, tb, cb);
+        st_row4(node + (int64_t)e1 * D, lane, r1);
+    }
+}
+
 __global__ void __launch_bounds__(32) o1_ordered_kernel(float *node, int size, const uint32_t *edges, int64_t n_edges,
                                                         const uint64_t *seeds, uint64_t base_seed, Sampler S,
                                                         int negative, float lr, bool quirk, const float *g_exp_table) {
@@ -491,8 +555,6 @@ __global__ void __launch_bounds__(32)
 
 }  // namespace
 
-bool g_force_generic_ordered = false;  // tests: comemb_set_tuning(.., .., 900) routes size 128 to the generic kernel
-
 // ---- launchers (called from capi.cu) -------------------------------------------------------------------------------------
 int launch_o2_ordered(float *node, float *ctx, int size, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
                       const uint64_t *seeds, uint64_t base_seed, const uint32_t *table, uint64_t table_len, int window,
@@ -522,6 +584,18 @@ int launch_o1_ordered(float *node, int size, const uint32_t *edges, int64_t n_ed
                       uint64_t base_seed, const uint32_t *table, uint64_t table_len, int negative, float lr, bool quirk,
                       cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
+    if (size == 128 && !g_force_generic_ordered) {  // register-resident fast path, same bits
+        switch (negative) {
+#define COMEMB_CASE(N)                                                                                              \
+    case N:                                                                                                         \
+        o1_ordered_d128_kernel<N><<<1, 32, 0, st>>>(node, edges, n_edges, seeds, base_seed, S, lr, quirk,           \
+                                                    comemb_lut_device());                                           \
+        return (int)cudaGetLastError();
+            COMEMB_CASE(1) COMEMB_CASE(2) COMEMB_CASE(3) COMEMB_CASE(4) COMEMB_CASE(5) COMEMB_CASE(6) COMEMB_CASE(7)
+#undef COMEMB_CASE
+            default: break;
+        }
+    }
     size_t smem = (EXP_TABLE_SIZE + (size_t)size) * sizeof(float);
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(o1_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

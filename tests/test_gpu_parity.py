@@ -76,6 +76,16 @@ def test_o2_ordered_generic_kernel_at_d128(K, golden, name):
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
 
 
+@pytest.mark.parametrize("name", ["o1_d128", "o1_d128_init_like_model"])
+def test_o1_ordered_generic_kernel_at_d128(K, golden, name):
+    from comemb_b200 import _lib
+    _lib.check(_lib.load().comemb_set_tuning(0, 0, 900))
+    try:
+        test_o1_ordered_bit_exact_vs_reference_golden(K, golden, name)
+    finally:
+        _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
+
+
 @pytest.mark.parametrize("name", sorted(cases.O1_CASES))
 def test_o1_ordered_bit_exact_vs_reference_golden(K, golden, name):
     c = cases.O1_CASES[name]
