@@ -150,6 +150,13 @@ int comemb_walks_csr(const int64_t *d_rowptr, const uint32_t *d_col, int64_t n, 
                      double alpha, uint64_t seed, int mode, int64_t first_walk, int64_t n_out, uint32_t *d_walks,
                      int32_t *d_lens, void *stream);
 
+/* Frequent-node down-sampling of device-resident walks: replaces the filter of prepare_sentences
+ * (utils/embedding.py:126-136) with Model.precalc_sampling's probabilities (ADSCModel/model.py:69-81).  In place: token t
+ * survives with probability d_keep_prob[t]; dropped tokens are removed (the walk shrinks), the tail becomes
+ * COMEMB_TOKEN_NONE, d_lens (optional) is updated.  Counter-based generator keyed by (seed, walk, position). */
+int comemb_downsample_walks(uint32_t *d_walks, int32_t *d_lens, int64_t n_walks, int path_length,
+                             const float *d_keep_prob, uint64_t seed, void *stream);
+
 /* ---- sampler tables: replaces Model.make_table (ADSCModel/model.py:97-122) ----------------------------------------------
  * h_counts: HOST double [vocab_size] (node degree by row; the O(vocab) run-boundary recurrence runs on the host with
  * the same libm pow() as CPython), d_table: DEVICE uint32 [table_size] filled by a kernel, with the reference's

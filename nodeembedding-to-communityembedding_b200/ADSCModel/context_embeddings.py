@@ -48,6 +48,15 @@ class Context2Vec(object):
         if isinstance(paths, tuple) and len(paths) == 2 and hasattr(paths[0], "is_cuda"):
             walks2d, lens = paths  # device walker output: [n, L] padded with TOKEN_NONE
             n_walks, L = walks2d.shape
+            if model.down_sampling:  # prepare_sentences' frequent-node filter, on the device
+                from .. import _lib
+                _, rows_, probs_ = model.id_index()
+                keep = torch.ones(model.vocab_size, dtype=torch.float32)
+                keep[torch.from_numpy(rows_)] = torch.from_numpy(probs_.astype(np.float32))
+                walks2d, lens = walks2d.clone(), lens.clone()
+                _lib.check(_lib.load().comemb_downsample_walks(
+                    _lib.ptr(walks2d), _lib.ptr(lens), n_walks, L, _lib.ptr(keep.to(dev)),
+                    int(np.random.randint(0, 2 ** 31)), _lib.stream_ptr()))
             walks = walks2d.reshape(-1)
             off = torch.arange(n_walks + 1, dtype=torch.int64, device=dev) * L
         else:

@@ -39,6 +39,7 @@ SIGNATURES = {
     "comemb_sg_twin": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _f64, _f64, _f64, _vp, _vp, _vp, _i32, _i32,
                               _vp]),
     "comemb_walks_csr": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _u64, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "comemb_downsample_walks": (_i32, [_vp, _vp, _i64, _i32, _vp, _u64, _vp]),
     "comemb_make_table": (_i32, [_vp, _i64, _f64, _vp, _i64, _vp]),
     "comemb_build_alias": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "comemb_scale": (_i32, [_vp, _i64, _f32, _vp]),

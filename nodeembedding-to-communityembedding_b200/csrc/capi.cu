@@ -39,6 +39,7 @@ int launch_o2_pos_loss(const float *, const float *, int, const uint32_t *, cons
                        cudaStream_t);
 int launch_walks(const int64_t *, const uint32_t *, int64_t, int, int, double, uint64_t, int, int64_t, int64_t,
                  uint32_t *, int32_t *, cudaStream_t);
+int launch_downsample_walks(uint32_t *, int32_t *, int64_t, int, const float *, uint64_t, cudaStream_t);
 int host_make_table(const double *, int64_t, double, uint32_t *, int64_t, cudaStream_t);
 int host_build_alias(const uint32_t *, int64_t, int64_t, uint32_t *, cudaStream_t);
 
@@ -263,6 +264,12 @@ int comemb_walks_csr(const int64_t *d_rowptr, const uint32_t *d_col, int64_t n, 
     if (mode != COMEMB_MODE_ORDERED && mode != COMEMB_MODE_HOGWILD) return COMEMB_E_ARG;
     return launch_walks(d_rowptr, d_col, n, num_paths, path_length, alpha, seed, mode, first_walk, n_out, d_walks,
                         d_lens, (cudaStream_t)stream);
+}
+
+int comemb_downsample_walks(uint32_t *d_walks, int32_t *d_lens, int64_t n_walks, int path_length,
+                             const float *d_keep_prob, uint64_t seed, void *stream) {
+    if (!d_walks || !d_keep_prob || n_walks < 0 || path_length < 0) return COMEMB_E_ARG;
+    return launch_downsample_walks(d_walks, d_lens, n_walks, path_length, d_keep_prob, seed, (cudaStream_t)stream);
 }
 
 int comemb_make_table(const double *h_counts, int64_t vocab_size, double power, uint32_t *d_table, int64_t table_size,

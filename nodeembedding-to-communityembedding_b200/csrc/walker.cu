@@ -150,7 +150,48 @@ __global__ void __launch_bounds__(256) walks_hogwild_kernel(const int64_t *__res
     for (int p = len; p < L; p++) path[p] = COMEMB_TOKEN_NONE;
 }
 
+// prepare_sentences' frequent-node down-sampling (utils/embedding.py:126-136) for walks that never leave the device:
+// token t is kept with probability keep_prob[t] (Model.precalc_sampling, model.py:69-81); dropped tokens are REMOVED
+// (the path gets shorter, as in the reference), the tail is padded with TOKEN_NONE.  One warp per walk, in place.
+__global__ void __launch_bounds__(256) downsample_walks_kernel(uint32_t *walks, int32_t *lens, int64_t n_walks, int L,
+                                                               const float *__restrict__ keep_prob, uint64_t seed) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= n_walks) return;
+    uint32_t *path = walks + w * L;
+    const int len = lens ? lens[w] : L;
+    const uint64_t key = splitmix64(seed ^ splitmix64((uint64_t)w + 0x2545F4914F6CDD1DULL));
+    int out = 0;
+    for (int base = 0; base < len; base += 32) {
+        const int i = base + lane;
+        uint32_t t = COMEMB_TOKEN_NONE;
+        bool keep = false;
+        if (i < len) {
+            t = path[i];
+            if (t != COMEMB_TOKEN_NONE) {
+                const float p = keep_prob[t];
+                const float u = (float)(splitmix64(key + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1)) >> 40) * (1.0f / 16777216.0f);
+                keep = p >= 1.0f || p >= u;  // embedding.py:135
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, keep);
+        __syncwarp();
+        if (keep) path[out + __popc(m & ((1u << lane) - 1u))] = t;  // out + rank <= i: never overtakes unread tokens
+        out += __popc(m);
+        __syncwarp();
+    }
+    for (int i = out + lane; i < L; i += 32) path[i] = COMEMB_TOKEN_NONE;
+    if (lens && lane == 0) lens[w] = out;
+}
+
 }  // namespace
+
+int launch_downsample_walks(uint32_t *walks, int32_t *lens, int64_t n_walks, int L, const float *keep_prob, uint64_t seed,
+                            cudaStream_t st) {
+    if (n_walks <= 0 || L <= 0) return 0;
+    downsample_walks_kernel<<<(unsigned)((n_walks + 7) / 8), 256, 0, st>>>(walks, lens, n_walks, L, keep_prob, seed);
+    return (int)cudaGetLastError();
+}
 
 int launch_walks(const int64_t *rowptr, const uint32_t *col, int64_t n, int num_paths, int L, double alpha,
                  uint64_t seed, int mode, int64_t first_walk, int64_t n_out, uint32_t *walks, int32_t *lens,

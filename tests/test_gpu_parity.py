@@ -945,3 +945,37 @@ def test_config3_blogcatalog_shape_full_training(K):
     assert torch.isfinite(model.node_embedding).all()
     com.fit(model)
     assert nmi(block, model.pi.argmax(1).cpu().numpy()) > q_head - 0.1
+
+
+def test_device_downsampling_of_walks(K):
+    """comemb_downsample_walks vs the definition: tokens with keep probability 1 always survive in order, tokens with
+    probability 0 never, probability p survives at rate p; the walk is compacted and padded with TOKEN_NONE."""
+    import torch
+    from comemb_b200 import _lib
+    n, L, nw = 100, 80, 5000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    walks = torch.randint(0, n, (nw, L), device="cuda", generator=g, dtype=torch.int32)
+    lens = torch.full((nw,), L, dtype=torch.int32, device="cuda")
+    lens[::3] = 50
+    keep = torch.ones(n, device="cuda")
+    keep[10:20] = 0.0
+    keep[20:30] = 0.25
+    orig = walks.clone()
+    _lib.check(_lib.load().comemb_downsample_walks(walks.data_ptr(), lens.data_ptr(), nw, L, keep.data_ptr(), 7, None))
+    o, w, ln = orig.cpu().numpy(), walks.cpu().numpy().view(np.uint32), lens.cpu().numpy()
+    kept25 = 0
+    seen25 = 0
+    for i in range(0, nw, 97):
+        src = o[i, :50 if i % 3 == 0 else L]
+        out = w[i, :ln[i]].astype(np.int64)
+        assert (w[i, ln[i]:] == cases.TOKEN_NONE).all()
+        assert not ((out >= 10) & (out < 20)).any()
+        sure = src[(src < 10) | (src >= 30)]
+        assert np.array_equal(out[(out < 10) | (out >= 30)], sure)  # certain tokens all survive, in order
+        it = iter(src.tolist())
+        assert all(any(t == s for s in it) for t in out.tolist())    # the output is a subsequence of the input
+    allsrc = o[np.arange(nw) % 3 != 0]
+    allout = w[np.arange(nw) % 3 != 0]
+    seen25 = ((allsrc >= 20) & (allsrc < 30)).sum()
+    kept25 = ((allout >= 20) & (allout < 30)).sum()
+    assert abs(kept25 / seen25 - 0.25) < 0.02
