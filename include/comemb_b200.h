@@ -114,6 +114,11 @@ int comemb_o1_edges(float *d_node, int64_t n_rows, int size, const uint32_t *d_e
 int comemb_o3_batch(float *d_node, int64_t n_rows, int size, const uint32_t *d_rows, int64_t n_sel,
                     const float *d_mu, const float *d_inv_cov_t, const float *d_pi, int K, double beta, float lr,
                     int iters, void *stream);
+/* The same update with pi in TOP-1 form (what fp32 predict_proba gives on separated data, and the only form that fits
+ * at 50M nodes x 1000 communities): d_comm[r] = the row's community or -1, d_weight[r] = its responsibility. */
+int comemb_o3_batch_top1(float *d_node, int64_t n_rows, int size, const uint32_t *d_rows, int64_t n_sel,
+                         const float *d_mu, const float *d_inv_cov_t, const int32_t *d_comm, const float *d_weight, int K,
+                         double beta, float lr, int iters, void *stream);
 /* out[k][b][a] = in[k][a][b] for K blocks of size x size */
 int comemb_transpose_blocks(const float *d_in, float *d_out, int K, int size, void *stream);
 
@@ -127,6 +132,14 @@ int comemb_sg_fused(float *d_node, float *d_negemb, int64_t n_rows, int size, co
                     const float *d_mu, const float *d_inv_cov, const float *d_pi, int K, int window, int negative,
                     float lr, float lambda1, float lambda2, int is_node_embedding, int mode, uint32_t flags,
                     void *stream);
+
+/* The fused pass (HOGWILD, tensor-core kernel: size 128, negative 3..5, window <= 12, context table != node table) with
+ * pi in top-1 form (see comemb_o3_batch_top1); no dense pi is needed. */
+int comemb_sg_fused_top1(float *d_node, float *d_negemb, int64_t n_rows, int size, const uint32_t *d_walks,
+                         const int64_t *d_walk_off, int64_t n_walks, const int32_t *d_reduced_windows,
+                         const uint64_t *d_seeds, uint64_t base_seed, const uint32_t *d_table, uint64_t table_len,
+                         const float *d_mu, const float *d_inv_cov, const int32_t *d_comm, const float *d_weight, int K,
+                         int window, int negative, float lr, float lambda1, float lambda2, uint32_t flags, void *stream);
 
 /* ---- Python-twin semantics of the fused pass: replaces the fallback train_sg / gradient_update / community_sdg of
  * utils/embedding.py:15-98 (exact sigmoid, negatives redrawn until != both nodes, vectorised update where duplicate

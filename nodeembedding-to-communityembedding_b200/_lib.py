@@ -33,6 +33,9 @@ SIGNATURES = {
     "comemb_o1_edges": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _u64, _vp, _u64, _vp, _u32, _i32, _f32, _i32, _u32,
                                _i64, _vp]),
     "comemb_o3_batch": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _f64, _f32, _i32, _vp]),
+    "comemb_o3_batch_top1": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _f64, _f32, _i32, _vp]),
+    "comemb_sg_fused_top1": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp,
+                                    _i32, _i32, _i32, _f32, _f32, _f32, _u32, _vp]),
     "comemb_transpose_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "comemb_sg_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32,
                                _i32, _i32, _f32, _f32, _f32, _i32, _i32, _u32, _vp]),

@@ -31,8 +31,10 @@ extern bool g_force_generic_fused;
 extern int64_t g_fused_n_rows;
 int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
                    const float *, const float *, const float *, int, int, cudaStream_t);
-int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const float *, const float *, const float *, int,
-                    double, float, int, cudaStream_t);
+int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const float *, const float *, const float *,
+                    const int32_t *, const float *, int, double, float, int, cudaStream_t);
+extern const int32_t *g_fused_comm;
+extern const float *g_fused_weight;
 int launch_transpose_blocks(const float *, float *, int, int, cudaStream_t);
 int launch_scale(float *, int64_t, float, cudaStream_t);
 int launch_o2_pos_loss(const float *, const float *, int, const uint32_t *, const int64_t *, int64_t, int, double *,
@@ -211,8 +213,19 @@ int comemb_o3_batch(float *d_node, int64_t n_rows, int size, const uint32_t *d_r
     if (!d_node || n_rows <= 0 || size <= 0 || K <= 0 || !d_mu || !d_inv_cov_t || !d_pi || iters < 0) return COMEMB_E_ARG;
     if (!d_rows) n_sel = n_rows;
     if (n_sel < 0) return COMEMB_E_ARG;
-    return launch_o3_batch(d_node, n_rows, size, d_rows, n_sel, d_mu, d_inv_cov_t, d_pi, K, beta, lr, iters,
-                           (cudaStream_t)stream);
+    return launch_o3_batch(d_node, n_rows, size, d_rows, n_sel, d_mu, d_inv_cov_t, d_pi, nullptr, nullptr, K, beta, lr,
+                           iters, (cudaStream_t)stream);
+}
+
+int comemb_o3_batch_top1(float *d_node, int64_t n_rows, int size, const uint32_t *d_rows, int64_t n_sel,
+                         const float *d_mu, const float *d_inv_cov_t, const int32_t *d_comm, const float *d_weight, int K,
+                         double beta, float lr, int iters, void *stream) {
+    if (!d_node || n_rows <= 0 || size <= 0 || K <= 0 || !d_mu || !d_inv_cov_t || !d_comm || !d_weight || iters < 0)
+        return COMEMB_E_ARG;
+    if (!d_rows) n_sel = n_rows;
+    if (n_sel < 0) return COMEMB_E_ARG;
+    return launch_o3_batch(d_node, n_rows, size, d_rows, n_sel, d_mu, d_inv_cov_t, nullptr, d_comm, d_weight, K, beta, lr,
+                           iters, (cudaStream_t)stream);
 }
 
 int comemb_transpose_blocks(const float *d_in, float *d_out, int K, int size, void *stream) {
@@ -255,6 +268,30 @@ int comemb_sg_twin(float *d_node, float *d_ctx, int64_t n_rows, int size, const 
     if (lambda2 > 0.0 && (K <= 0 || !d_mu || !d_inv_cov || !d_pi)) return COMEMB_E_ARG;
     return launch_sg_twin(d_node, d_ctx, size, d_pair_row, d_targets, n_pairs, negative, alpha, lambda1, lambda2, d_mu,
                           d_inv_cov, d_pi, K, is_node_embedding, (cudaStream_t)stream);
+}
+
+int comemb_sg_fused_top1(float *d_node, float *d_negemb, int64_t n_rows, int size, const uint32_t *d_walks,
+                         const int64_t *d_walk_off, int64_t n_walks, const int32_t *d_reduced_windows,
+                         const uint64_t *d_seeds, uint64_t base_seed, const uint32_t *d_table, uint64_t table_len,
+                         const float *d_mu, const float *d_inv_cov, const int32_t *d_comm, const float *d_weight, int K,
+                         int window, int negative, float lr, float lambda1, float lambda2, uint32_t flags, void *stream) {
+    REQUIRE_INIT();
+    if (!d_node || !d_negemb || d_node == d_negemb || n_rows <= 0 || size != 128 || n_walks < 0 || window < 0 ||
+        2 * window > 24 || negative < 3 || negative > 5 || !d_comm || !d_weight || !d_mu || !d_inv_cov || K <= 0)
+        return COMEMB_E_UNSUPPORTED;  // this entry exists for the tensor-core kernel only
+    if (n_walks > 0 && (!d_walks || !d_walk_off)) return COMEMB_E_ARG;
+    if (!d_table || table_len == 0) return COMEMB_E_ARG;
+    if (!d_seeds && !(flags & COMEMB_F_SEED_HASH)) return COMEMB_E_ARG;
+    if (n_walks == 0) return 0;
+    g_fused_n_rows = n_rows;
+    g_fused_comm = d_comm;
+    g_fused_weight = d_weight;
+    const int e = launch_sg_fused_hogwild(d_node, d_negemb, size, d_walks, d_walk_off, n_walks, d_reduced_windows, d_seeds,
+                                          base_seed, d_table, table_len, d_mu, d_inv_cov, nullptr, K, window, negative, lr,
+                                          lambda1, lambda2, 0, (flags & COMEMB_F_ATOMIC) != 0, (cudaStream_t)stream);
+    g_fused_comm = nullptr;
+    g_fused_weight = nullptr;
+    return e;
 }
 
 int comemb_walks_csr(const int64_t *d_rowptr, const uint32_t *d_col, int64_t n, int num_paths, int path_length,

@@ -17,6 +17,8 @@
 int64_t hogwild_get_max_warps();
 extern int64_t g_fused_n_rows;
 extern bool g_force_generic_fused;
+extern const int32_t *g_fused_comm;
+extern const float *g_fused_weight;
 
 namespace {
 
@@ -579,6 +581,8 @@ int launch_fast(const SgFastParams &F, int negative, bool atomic, cudaStream_t s
 }  // namespace
 
 int64_t g_fused_n_rows = 0;           // set by comemb_sg_fused (the one-hot scan needs the row count of pi)
+const int32_t *g_fused_comm = nullptr;  // comemb_sg_fused_top1: caller-provided top-1 form of pi (no dense pi at all)
+const float *g_fused_weight = nullptr;
 bool g_force_generic_fused = false;   // tests: comemb_set_tuning(.., .., 900)
 
 int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t *walks, const int64_t *walk_off,
@@ -595,12 +599,13 @@ int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t
     P.lr = lr; P.lambda1 = lambda1; P.lambda2 = lambda2; P.is_node_embedding = is_node_embedding;
     P.glut = comemb_lut_device();
     // fast path: size 128, NEG in {3,4,5}, separate context table, window <= 12, pi one-hot (or lambda2 == 0)
+    const bool top1 = g_fused_comm != nullptr;  // the caller already holds pi in top-1 form (and no dense pi)
     if (size == 128 && !is_node_embedding && negemb != node && 2 * window <= VMAX && negative >= 3 && negative <= 5 &&
-        !g_force_generic_fused) {
+        (!g_force_generic_fused || top1)) {
         int32_t *comm = nullptr;
         float *weight = nullptr;
         bool ok = true;
-        if (lambda2 != 0.f) {
+        if (lambda2 != 0.f && !top1) {
             int *flag = nullptr, h_flag = 0;
             const int64_t n_rows = g_fused_n_rows;
             if (n_rows <= 0) ok = false;
@@ -626,7 +631,8 @@ int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t
             SgFastParams F;
             F.node = node; F.ctx = negemb; F.walks = walks; F.walk_off = walk_off; F.n_walks = n_walks;
             F.rw = reduced_windows; F.seeds = seeds; F.base_seed = base_seed; F.table = table; F.mod = P.mod;
-            F.mu = mu; F.inv_cov = inv_r ? inv_r : inv_cov; F.comm = comm; F.weight = weight; F.window = window;
+            F.mu = mu; F.inv_cov = inv_r ? inv_r : inv_cov;
+            F.comm = top1 ? g_fused_comm : comm; F.weight = top1 ? g_fused_weight : weight; F.window = window;
             F.lr = lr; F.lambda1 = lambda1; F.lambda2 = lambda2; F.glut = P.glut;
             const int e = launch_fast(F, negative, atomic, st);
             if (inv_r) CUDA_TRY(cudaFreeAsync(inv_r, st));
@@ -637,6 +643,7 @@ int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t
         if (comm) CUDA_TRY(cudaFreeAsync(comm, st));
         if (weight) CUDA_TRY(cudaFreeAsync(weight, st));
     }
+    if (top1) return COMEMB_E_UNSUPPORTED;  // the generic kernel needs the dense pi
     if (size <= 128) return launch_t<1>(P, atomic, st);
     if (size <= 256) return launch_t<2>(P, atomic, st);
     return launch_t<4>(P, atomic, st);

@@ -21,7 +21,8 @@ constexpr int O3_MAX_SLICES = 16;  // size <= 512
 
 __global__ void __launch_bounds__(O3_WARPS * 32)
     o3_batch_kernel(float *node, int64_t n_rows, int size, const uint32_t *rows, int64_t n_sel, const float *mu,
-                    const float *inv_cov_t, const float *pi, int K, float scale, float lr, int iters) {
+                    const float *inv_cov_t, const float *pi, const int32_t *comm, const float *weight, int K,
+                    float scale, float lr, int iters) {
     extern __shared__ float smem[];
     float *diff = smem + (size_t)(threadIdx.x >> 5) * size;  // this warp's (x - mu_k)
     const int lane = threadIdx.x & 31;
@@ -31,13 +32,16 @@ __global__ void __launch_bounds__(O3_WARPS * 32)
     for (int64_t s = warp0; s < n_sel; s += n_warps) {
         const int64_t r = rows ? (int64_t)rows[s] : s;
         float *x = node + r * size;
-        const float *p_row = pi + r * K;
+        // dense pi row, or the top-1 form (one community + weight per row; comm < 0: no community)
+        const float *p_row = pi ? pi + r * K : nullptr;
+        const int only = pi ? -1 : comm[r];
+        const float only_w = pi ? 0.f : weight[r];
         for (int it = 0; it < iters; it++) {
             float grad[O3_MAX_SLICES];
 #pragma unroll
             for (int m = 0; m < O3_MAX_SLICES; m++) grad[m] = 0.f;
-            for (int k = 0; k < K; k++) {
-                const float p = p_row[k];
+            for (int k = (pi ? 0 : max(only, 0)); k < (pi ? K : only + 1); k++) {
+                const float p = pi ? p_row[k] : only_w;
                 if (p == 0.f) continue;
                 __syncwarp();
                 for (int b = lane; b < size; b += 32) diff[b] = x[b] - mu[(int64_t)k * size + b];  // :68
@@ -134,7 +138,8 @@ __global__ void __launch_bounds__(256) o2_pos_loss_kernel(const float *node, con
 }  // namespace
 
 int launch_o3_batch(float *node, int64_t n_rows, int size, const uint32_t *rows, int64_t n_sel, const float *mu,
-                    const float *inv_cov_t, const float *pi, int K, double beta, float lr, int iters, cudaStream_t st) {
+                    const float *inv_cov_t, const float *pi, const int32_t *comm, const float *weight, int K,
+                    double beta, float lr, int iters, cudaStream_t st) {
     if (size > 32 * O3_MAX_SLICES) return COMEMB_E_UNSUPPORTED;
     if (n_sel <= 0 || iters <= 0) return 0;
     const float scale = (float)(beta / (double)K);  // numpy: float32 array *= python float (beta/k)
@@ -144,7 +149,7 @@ int launch_o3_batch(float *node, int64_t n_rows, int size, const uint32_t *rows,
     int64_t want = (n_sel + O3_WARPS - 1) / O3_WARPS;
     int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     size_t smem = (size_t)O3_WARPS * size * sizeof(float);
-    o3_batch_kernel<<<grid, O3_WARPS * 32, smem, st>>>(node, n_rows, size, rows, n_sel, mu, inv_cov_t, pi, K, scale, lr,
+    o3_batch_kernel<<<grid, O3_WARPS * 32, smem, st>>>(node, n_rows, size, rows, n_sel, mu, inv_cov_t, pi, comm, weight, K, scale, lr,
                                                        iters);
     return (int)cudaGetLastError();
 }

@@ -274,6 +274,42 @@ def o3_batch(node, rows, centroid, inv_cov_t, pi, beta, lr, iters=1):
     _lib.check(st)
 
 
+def pi_top1(pi):
+    """Dense responsibilities [N,K] -> (comm int32 [N], weight float32 [N]): the single non-zero community of each row
+    (-1 / 0.0 for all-zero rows).  Raises if a row has more than one non-zero entry."""
+    torch = _torch()
+    nz = pi != 0
+    cnt = nz.sum(1)
+    if bool((cnt > 1).any()):
+        raise ComembError("pi is not one-hot: %d rows have several non-zero responsibilities" % int((cnt > 1).sum()))
+    comm = torch.where(cnt == 1, nz.float().argmax(1), torch.full_like(cnt, -1)).to(torch.int32)
+    weight = pi.sum(1).to(torch.float32)
+    return comm.contiguous(), weight.contiguous()
+
+
+def o3_batch_top1(node, rows, centroid, inv_cov_t, comm, weight, beta, lr, iters=1):
+    """o3_batch with pi in top-1 form (see pi_top1)."""
+    st = _lib.load().comemb_o3_batch_top1(
+        _lib.ptr(node), node.shape[0], node.shape[1], _lib.ptr(rows), 0 if rows is None else rows.numel(),
+        _lib.ptr(centroid), _lib.ptr(inv_cov_t), _lib.ptr(comm), _lib.ptr(weight), centroid.shape[0], float(beta),
+        float(lr), int(iters), _lib.stream_ptr())
+    _lib.check(st)
+
+
+def sg_batch_top1(node, negemb, walks, walk_off, reduced_windows, seeds, lr, negative, window, table, centroid, inv_cov,
+                  comm, weight, lambda1, lambda2, flags=0, base_seed=0):
+    """The fused pass (Hogwild, tensor-core kernel) with pi in top-1 form: no dense [N,K] matrix is needed."""
+    _lib.ensure_init()
+    if seeds is None:
+        flags |= F_SEED_HASH
+    st = _lib.load().comemb_sg_fused_top1(
+        _lib.ptr(node), _lib.ptr(negemb), node.shape[0], node.shape[1], _lib.ptr(walks), _lib.ptr(walk_off),
+        int(walk_off.numel()) - 1, _lib.ptr(reduced_windows), _lib.ptr(seeds), int(base_seed), _lib.ptr(table),
+        table.numel(), _lib.ptr(centroid), _lib.ptr(inv_cov), _lib.ptr(comm), _lib.ptr(weight), centroid.shape[0],
+        int(window), int(negative), float(lr), float(lambda1), float(lambda2), int(flags), _lib.stream_ptr())
+    _lib.check(st)
+
+
 def sg_batch(node, negemb, walks, walk_off, reduced_windows, seeds, lr, negative, window, table, centroid, inv_cov, pi,
              lambda1, lambda2, is_node_embedding, mode=MODE_ORDERED, flags=0, base_seed=0):
     """The legacy fused pass (stale train_sg) over a corpus."""

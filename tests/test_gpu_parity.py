@@ -979,3 +979,28 @@ def test_device_downsampling_of_walks(K):
     seen25 = ((allsrc >= 20) & (allsrc < 30)).sum()
     kept25 = ((allout >= 20) & (allout < 30)).sum()
     assert abs(kept25 / seen25 - 0.25) < 0.02
+
+
+def test_top1_forms_of_pi_equal_the_dense_forms(K):
+    """o3 and the fused pass with pi given as (community, weight) per row -- the only form that fits at BASELINE
+    config-5 scale (50M x 1000 dense pi = 200 GB) -- against the dense one-hot pi: o3 bit-identical; fused pass
+    bit-identical when run one walk per launch (same kernel, same operands)."""
+    import torch
+    node, ctx, table, mu, inv, pi, walks = _fast_sg_inputs(21)
+    comm, weight = K.pi_top1(dev(pi))
+    assert int((comm < 0).sum()) == int((pi.sum(1) == 0).sum())
+    a, b = dev(node), dev(node)
+    inv_t = K.transpose_blocks(dev(inv))
+    K.o3_batch(a, None, dev(mu), inv_t, dev(pi), 0.1, 0.05, iters=2)
+    K.o3_batch_top1(b, None, dev(mu), inv_t, comm, weight, 0.1, 0.05, iters=2)
+    assert torch.equal(a, b) and not torch.equal(a, dev(node))
+    seeds = O.seeds_from_numpy(np.random.RandomState(2), len(walks))
+    n1, c1, n2, c2 = dev(node), dev(ctx), dev(node), dev(ctx)
+    for w, s in zip(walks, seeds):
+        args = (dev(w), dev(np.array([0, len(w)], np.int64)), None, dev(np.array([s], np.uint64)), 0.025, 5, 5,
+                dev(table), dev(mu), dev(inv))
+        K.sg_batch(n1, c1, *args, dev(pi), 1.0, 0.3, 0, mode=K.MODE_HOGWILD)
+        K.sg_batch_top1(n2, c2, *args, comm, weight, 1.0, 0.3)
+    assert torch.equal(n1, n2) and torch.equal(c1, c2)
+    with pytest.raises(K.ComembError):
+        K.pi_top1(dev(np.full((4, 3), 1 / 3, np.float32)))
