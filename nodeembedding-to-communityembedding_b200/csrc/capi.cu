@@ -6,7 +6,7 @@
 
 
 // launchers implemented in the other translation units
-int launch_o2_ordered(float *, float *, int, const uint32_t *, const int64_t *, int64_t, const uint64_t *, uint64_t,
+int launch_o2_ordered(float *, float *, int64_t, int, const uint32_t *, const int64_t *, int64_t, const uint64_t *, uint64_t,
                       const uint32_t *, uint64_t, int, int, float, float, bool, int64_t *, cudaStream_t);
 int launch_o1_ordered(float *, int, const uint32_t *, int64_t, const uint64_t *, uint64_t, const uint32_t *, uint64_t,
                       int, float, bool, cudaStream_t);
@@ -27,6 +27,7 @@ int launch_o2_hogwild_sharded(float *const *, float *const *, int, int64_t, int,
                               cudaStream_t);
 void hogwild_set_max_warps(int64_t);
 extern bool g_force_generic_ordered;
+extern int g_ordered_variant;
 extern bool g_force_generic_fused;
 extern int64_t g_fused_n_rows;
 int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
@@ -110,6 +111,7 @@ int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm)
     if (centres_per_unit < 0 || max_walk_len < 0 || blocks_per_sm < 0) return COMEMB_E_ARG;
     hogwild_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm);
     g_force_generic_ordered = (blocks_per_sm / 100) == 9;
+    g_ordered_variant = ((blocks_per_sm / 100) == 7 || (blocks_per_sm / 100) == 8) ? blocks_per_sm / 100 : 0;
     g_force_generic_fused = (blocks_per_sm / 100) == 9;
     return 0;
 }
@@ -133,7 +135,7 @@ int comemb_o2_walks(float *d_node, float *d_ctx, int64_t n_rows, int size, const
     cudaStream_t st = (cudaStream_t)stream;
     if (n_walks == 0) return 0;
     if (mode == COMEMB_MODE_ORDERED)
-        return launch_o2_ordered(d_node, d_ctx, size, d_walks, d_walk_off, n_walks, d_seeds, base_seed, d_table,
+        return launch_o2_ordered(d_node, d_ctx, n_rows, size, d_walks, d_walk_off, n_walks, d_seeds, base_seed, d_table,
                                  table_len, window, negative, lr, lambda, !(flags & COMEMB_F_DOT_FLOAT), d_n_tokens, st);
     if (mode == COMEMB_MODE_HOGWILD)
         return launch_o2_hogwild(d_node, d_ctx, size, d_walks, d_walk_off, n_walks, d_seeds, base_seed, d_table,

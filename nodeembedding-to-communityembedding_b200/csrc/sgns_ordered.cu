@@ -13,6 +13,8 @@
 #include "comemb_common.cuh"
 
 bool g_force_generic_ordered = false;  // tests: comemb_set_tuning(.., .., 900) routes size 128 to the generic kernels
+int g_ordered_variant = 0;  // comemb_set_tuning(.., .., 100*v): size-128 ORDERED kernels -- 0: one warp per target row (o2) /
+                            // pipelined (o1); 7: single warp, software-pipelined; 8: single warp, plain
 
 namespace {
 
@@ -311,6 +313,430 @@ __global__ void __launch_bounds__(32)
     if (n_tokens && lane == 0) *n_tokens += tokens;
 }
 
+// ---- o2 ORDERED, size == 128, register-resident AND software-pipelined -----------------------------------------------------
+// Same arithmetic as o2_ordered_d128_kernel; the difference is when the loads are issued.  A single warp replaying a
+// sequential stream is bound by memory latency (row gather -> dots -> scatter -> next gather), so the rows of pair p+1
+// (its node row and, inside one centre's window, its NEG sampled context rows) are requested BEFORE pair p is computed
+// and the samples of pair p+2 before that.  Exactness is kept by explicit hazard checks: a prefetched row that pair p
+// writes (same walk token, or a sample equal to one of pair p's samples) is replaced by the register copy / re-read
+// after pair p's stores, and nothing is prefetched across a centre change (the positive row lives in registers until
+// then).  Requires node and ctx not to overlap (the launcher checks; otherwise the kernel above is used).
+template <int NEG>
+__global__ void __launch_bounds__(32)
+    o2_ordered_d128_pipe_kernel(float *node, float *ctx, const uint32_t *walks, const int64_t *walk_off,
+                                int64_t n_walks, const uint64_t *seeds, uint64_t base_seed, Sampler S, int window,
+                                float lr, float lambda, bool quirk, int64_t *n_tokens, const float *g_exp_table) {
+    constexpr int D = 128;
+    constexpr LcgJump<NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    extern __shared__ uint32_t path[];  // [MAX_SENTENCE_LEN] tokens of the current walk
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
+    __syncwarp();
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    int64_t tokens = 0;
+    for (int64_t w = 0; w < n_walks; w++) {
+        const int len = (int)min((int64_t)MAX_SENTENCE_LEN, walk_off[w + 1] - walk_off[w]);
+        {  // tokens go to shared memory: a global token load would wait behind the row requests in flight
+            const uint32_t *gpath = walks + walk_off[w];
+            __syncwarp();
+            int cnt = 0;
+            for (int e = lane; e < len; e += 32) {
+                const uint32_t tok = gpath[e];
+                path[e] = tok;
+                cnt += (tok != COMEMB_TOKEN_NONE);
+            }
+            __syncwarp();
+            tokens += __reduce_add_sync(FULL, cnt);
+        }
+        uint64_t rnd = seeds ? seeds[w] : (splitmix64(base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        auto fetch = [&]() -> uint32_t {  // the next NEG samples of the stream, one per lane (pyx:133-134)
+            const uint32_t v = (lane < NEG) ? S.table[table_slot((myA * rnd + myC) & LCG_MASK, S.mod)] : 0u;
+            rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+            return v;
+        };
+        // first valid (centre i, context j) at or after the candidate position, in the reference's order (pyx:494-507)
+        auto seek = [&](int &i, int &j, uint32_t &wi, uint32_t &wj) -> bool {
+            while (i < len) {
+                if (wi != COMEMB_TOKEN_NONE) {
+                    const int j1 = min(len, i + window + 1);
+                    for (; j < j1; j++) {
+                        if (j == i) continue;
+                        wj = path[j];
+                        if (wj != COMEMB_TOKEN_NONE) return true;
+                    }
+                }
+                i++;
+                if (i < len) {
+                    wi = path[i];
+                    j = max(0, i - window);
+                }
+            }
+            return false;
+        };
+        int i = 0, j = 0;
+        uint32_t wi = len > 0 ? path[0] : COMEMB_TOKEN_NONE, wj = 0;
+        if (!seek(i, j, wi, wj)) continue;
+        uint32_t tq_cur = fetch();
+        uint32_t tq_nxt = fetch();
+        Row4 cpos = ld_row4(ctx + (int64_t)wi * D, lane);
+        Row4 x = ld_row4(node + (int64_t)wj * D, lane);
+        uint32_t t[NEG];
+        Row4 c[NEG];
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            t[k] = __shfl_sync(FULL, tq_cur, k);
+            c[k] = ld_row4(ctx + (int64_t)t[k] * D, lane);
+        }
+        for (;;) {
+            // ---- look ahead: pair p+1, its rows, and the samples of pair p+2 ----
+            int ni = i, nj = j + 1;
+            uint32_t nwi = wi, nwj = 0;
+            const bool nvalid = seek(ni, nj, nwi, nwj);
+            const bool same = nvalid && ni == i;
+            uint32_t tn[NEG];
+            Row4 cn[NEG];
+            Row4 xn = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < NEG; k++) tn[k] = __shfl_sync(FULL, tq_nxt, k);
+            const uint32_t tq_new = fetch();
+            if (nvalid) xn = ld_row4(node + (int64_t)nwj * D, lane);
+            bool stale = !same;
+#pragma unroll
+            for (int k = 0; k < NEG; k++) cn[k] = c[k];
+            if (same) {
+#pragma unroll
+                for (int k = 0; k < NEG; k++) cn[k] = ld_row4(ctx + (int64_t)tn[k] * D, lane);
+#pragma unroll
+                for (int k = 0; k < NEG; k++)
+#pragma unroll
+                    for (int m = 0; m < NEG; m++) stale = stale || (tn[k] == t[m]);
+            }
+            // ---- pair p (fast_o2, pyx:105-151) ----
+            bool anydup = false;
+#pragma unroll
+            for (int k = 1; k < NEG; k++)
+#pragma unroll
+                for (int a = 0; a < k; a++) anydup = anydup || (t[a] == t[k]);
+            Row4 work = {0.f, 0.f, 0.f, 0.f};  // pyx:126
+            {
+                const float f = dot128_refblas(x, cpos, quirk);
+                if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+                    const float g = __fmul_rn(__fmul_rn(1.f - lut[lut_index(f)], lr), lambda);
+                    fma_row4(work, g, cpos);  // pyx:146
+                    fma_row4(cpos, g, x);     // pyx:147
+                }
+            }
+            if (!anydup) {
+                float f[NEG];
+#pragma unroll
+                for (int k = 0; k < NEG; k++) f[k] = dot128_refblas(x, c[k], quirk);
+#pragma unroll
+                for (int k = 0; k < NEG; k++) {
+                    if (t[k] == wi) continue;                                // pyx:135-136
+                    if (f[k] <= -MAX_EXP_F || f[k] >= MAX_EXP_F) continue;  // pyx:141-142
+                    const float g = __fmul_rn(__fmul_rn(0.f - lut[lut_index(f[k])], lr), lambda);
+                    fma_row4(work, g, c[k]);
+                    fma_row4(c[k], g, x);
+                    st_row4(ctx + (int64_t)t[k] * D, lane, c[k]);
+                }
+            } else {  // equal samples inside one pair: strictly one after the other, re-reading the row
+#pragma unroll 1
+                for (int k = 0; k < NEG; k++) {
+                    const uint32_t tk = __shfl_sync(FULL, tq_cur, k);
+                    if (tk == wi) continue;
+                    float *cp = ctx + (int64_t)tk * D;
+                    Row4 cc = ld_row4(cp, lane);
+                    const float f = dot128_refblas(x, cc, quirk);
+                    if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
+                    const float g = __fmul_rn(__fmul_rn(0.f - lut[lut_index(f)], lr), lambda);
+                    fma_row4(work, g, cc);
+                    fma_row4(cc, g, x);
+                    st_row4(cp, lane, cc);
+                }
+            }
+            const Row4 nx = {x.v0 + work.v0, x.v1 + work.v1, x.v2 + work.v2, x.v3 + work.v3};  // pyx:149
+            st_row4(node + (int64_t)wj * D, lane, nx);
+            if (!nvalid) {
+                st_row4(ctx + (int64_t)wi * D, lane, cpos);
+                break;
+            }
+            // ---- hazards, then rotate ----
+            if (nwj == wj) xn = nx;
+            if (!same) {
+                st_row4(ctx + (int64_t)wi * D, lane, cpos);
+                cpos = ld_row4(ctx + (int64_t)nwi * D, lane);
+            }
+            if (stale) {
+#pragma unroll
+                for (int k = 0; k < NEG; k++) cn[k] = ld_row4(ctx + (int64_t)tn[k] * D, lane);
+            }
+            x = xn;
+#pragma unroll
+            for (int k = 0; k < NEG; k++) {
+                c[k] = cn[k];
+                t[k] = tn[k];
+            }
+            tq_cur = tq_nxt;
+            tq_nxt = tq_new;
+            i = ni; j = nj; wi = nwi; wj = nwj;
+        }
+    }
+    if (n_tokens && lane == 0) *n_tokens += tokens;
+}
+
+// ---- o2 ORDERED, size == 128: one warp PER TARGET ROW of a pair (NEG+1 warps), still strictly sequential over pairs -------
+// A single warp replaying the stream is bound by instruction latency (about 570 dependent-ish instructions per pair, no
+// other warp to hide them).  The NEG+1 targets of one pair are independent of each other unless two samples coincide,
+// so warp 0 owns the centre's context row (registers, across the window) and warp r>0 owns sample r-1: phase A (all
+// warps in parallel) dot -> sigma -> g, publish (g, old target row) in shared memory, update + store the target row;
+// one CTA barrier; phase B (every warp, redundantly, so that each has the new node row for forwarding) accumulates
+// `work` in the reference's order d = 0..NEG and forms x + work; warp 0 stores it.
+// Rows are requested two pairs ahead and samples four pairs ahead with cp.async into per-warp shared-memory rings
+// (register prefetch does not work at this depth: the load scoreboard is a counter, so touching the oldest request
+// waits for the youngest).  A request for pair p+2 is issued after barrier p, which makes the stores of pairs <= p
+// visible; a requested row that pair p+1 writes is re-read at the start of pair p+2 (hazard flag), node rows of the two
+// pairs in flight are forwarded from registers.  A pair with two equal samples is executed by warp 0 alone, one target
+// after the other.  Every floating-point operation and its order is the one of o2_ordered_d128_kernel: same bits.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ Row4 lds_row4(const float *row, int lane) {
+    Row4 v;
+    v.v0 = row[lane]; v.v1 = row[lane + 32]; v.v2 = row[lane + 64]; v.v3 = row[lane + 96];
+    return v;
+}
+
+template <int NEG>
+__global__ void __launch_bounds__(32 * (NEG + 1), 1)
+    o2_ordered_d128_team_kernel(float *node, float *ctx, const uint32_t *walks, const int64_t *walk_off,
+                                int64_t n_walks, const uint64_t *seeds, uint64_t base_seed, Sampler S, int window,
+                                float lr, float lambda, bool quirk, int64_t *n_tokens, const float *g_exp_table) {
+    constexpr int D = 128;
+    constexpr int NT = NEG + 1;
+    constexpr LcgJump<NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    __shared__ float4 stage[2][NT][32];  // old target rows of the pair (Row4 layout), or x + work in serial mode
+    __shared__ float gs[2][NT];
+    __shared__ int used[2][NT];
+    __shared__ __align__(16) float xring[NT][3][D];  // per warp: node row of pairs p, p+1, p+2
+    __shared__ __align__(16) float cring[NT][3][D];  // per warp: own sample row of pairs p, p+1, p+2
+    __shared__ uint32_t tring[NT][8][32];            // per warp: samples of pairs p .. p+4 (lane k = sample k)
+    extern __shared__ uint32_t path[];               // [MAX_SENTENCE_LEN] tokens of the current walk
+    const int lane = threadIdx.x & 31;
+    const int r = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += 32 * NT) lut[e] = g_exp_table[e];
+    for (int q = 0; q < 8; q++) tring[r][q][lane] = COMEMB_TOKEN_NONE;  // lanes >= NEG keep a value no row has
+    __syncthreads();
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    const int ks = r > 0 ? r - 1 : 0;  // own target row: warp 0 -> ctx[wi] (cpos), warp r -> ctx[sample r-1]
+    int64_t tokens = 0;
+    for (int64_t w = 0; w < n_walks; w++) {
+        const int len = (int)min((int64_t)MAX_SENTENCE_LEN, walk_off[w + 1] - walk_off[w]);
+        __syncthreads();  // every store of the previous walk is visible; `path`, rings and stages are free
+        {
+            const uint32_t *gpath = walks + walk_off[w];
+            for (int e = threadIdx.x; e < len; e += 32 * NT) path[e] = gpath[e];
+        }
+        __syncthreads();
+        if (r == 0) {
+            int cnt = 0;
+            for (int e = lane; e < len; e += 32) cnt += (path[e] != COMEMB_TOKEN_NONE);
+            tokens += __reduce_add_sync(FULL, cnt);
+        }
+        uint64_t rnd = seeds ? seeds[w] : (splitmix64(base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        auto request_samples = [&](int q) {  // samples of pair q -> tring[.][q & 7] (pyx:133-134)
+            if (lane < NEG) cp_async4(&tring[r][q & 7][lane], S.table + table_slot((myA * rnd + myC) & LCG_MASK, S.mod));
+            rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+        };
+        auto seek = [&](int &i, int &j, uint32_t &wi, uint32_t &wj) -> bool {  // pyx:494-507
+            while (i < len) {
+                if (wi != COMEMB_TOKEN_NONE) {
+                    const int j1 = min(len, i + window + 1);
+                    for (; j < j1; j++) {
+                        if (j == i) continue;
+                        wj = path[j];
+                        if (wj != COMEMB_TOKEN_NONE) return true;
+                    }
+                }
+                i++;
+                if (i < len) {
+                    wi = path[i];
+                    j = max(0, i - window);
+                }
+            }
+            return false;
+        };
+        // pairs p (0), p+1 (1), p+2 (2)
+        int i0 = 0, j0 = 0;
+        uint32_t wi0 = len > 0 ? path[0] : COMEMB_TOKEN_NONE, wj0 = 0;
+        if (!seek(i0, j0, wi0, wj0)) continue;
+        int i1 = i0, j1 = j0 + 1;
+        uint32_t wi1 = wi0, wj1 = 0;
+        bool v1 = seek(i1, j1, wi1, wj1);
+        // prologue: samples of pairs 0..3, then the rows of pairs 0 and 1 (one cp.async group each)
+        request_samples(0); request_samples(1); request_samples(2); request_samples(3);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        cp_async16(&xring[r][0][4 * lane], node + (int64_t)wj0 * D + 4 * lane);
+        if (r > 0) cp_async16(&cring[r][0][4 * lane], ctx + (int64_t)__shfl_sync(FULL, tring[r][0][lane], ks) * D + 4 * lane);
+        cp_async_commit();
+        if (v1) cp_async16(&xring[r][1][4 * lane], node + (int64_t)wj1 * D + 4 * lane);
+        cp_async_commit();
+        bool hz0 = false;
+        bool hz1 = true;     // pair 1's sample row is read at its start (after barrier 0); once per walk
+        bool newc = true;    // warp 0: read the centre's context row at the start of the pair
+        Row4 cpos = {0.f, 0.f, 0.f, 0.f};
+        Row4 nx1 = cpos, nx2 = cpos;                       // x + work of pairs p-1, p-2
+        uint32_t wjm1 = COMEMB_TOKEN_NONE, wjm2 = COMEMB_TOKEN_NONE;  // their rows
+        int s = 0, p3 = 0;  // p3 = p mod 3
+        for (int p = 0;; p++) {
+            const int pc = p3 == 0 ? 2 : p3 - 1;  // (p + 2) mod 3
+            // ---- start of pair p: its requests have landed (at most the youngest group may be pending) ----
+            cp_async_wait<1>();
+            __syncwarp();
+            const uint32_t tq0 = tring[r][p & 7][lane];
+            const uint32_t u0 = __shfl_sync(FULL, tq0, ks);
+            Row4 x0;
+            if (wj0 == wjm1) x0 = nx1;
+            else if (wj0 == wjm2) x0 = nx2;
+            else x0 = lds_row4(xring[r][p3], lane);
+            Row4 c0;
+            if (r == 0) {
+                if (newc) cpos = ld_row4(ctx + (int64_t)wi0 * D, lane);  // after barrier p-1: everything visible
+                c0 = cpos;
+            } else {
+                if (hz0) c0 = ld_row4(ctx + (int64_t)u0 * D, lane);
+                else c0 = lds_row4(cring[r][p3], lane);
+            }
+            // ---- look ahead: position of pair p+2, samples of pair p+4 ----
+            int i2 = i1, j2 = j1 + 1;
+            uint32_t wi2 = wi1, wj2 = 0;
+            const bool v2 = v1 && seek(i2, j2, wi2, wj2);
+            request_samples(p + 4);
+            const bool last_of_centre = !v1 || i1 != i0;
+            // two equal samples inside this pair -> serial execution by warp 0
+            const unsigned eq = __match_any_sync(FULL, tq0);
+            const bool serial = __any_sync(FULL, lane < NEG && (eq & ((1u << lane) - 1u)) != 0u);
+            // ---- phase A ----
+            Row4 nx;
+            if (!serial) {
+                bool use = !(r > 0 && u0 == wi0);  // pyx:135-136
+                float g = 0.f;
+                if (use) {
+                    const float f = dot128_refblas(x0, c0, quirk);
+                    use = f > -MAX_EXP_F && f < MAX_EXP_F;  // pyx:141-142
+                    if (use) g = __fmul_rn(__fmul_rn((r == 0 ? 1.f : 0.f) - lut[lut_index(f)], lr), lambda);
+                }
+                if (lane == 0) {
+                    gs[s][r] = g;
+                    used[s][r] = use ? 1 : 0;
+                }
+                if (use) {
+                    stage[s][r][lane] = make_float4(c0.v0, c0.v1, c0.v2, c0.v3);
+                    fma_row4(c0, g, x0);  // pyx:147
+                    if (r > 0) st_row4(ctx + (int64_t)u0 * D, lane, c0);
+                    else cpos = c0;
+                }
+                if (r == 0 && last_of_centre) st_row4(ctx + (int64_t)wi0 * D, lane, cpos);
+            } else if (r == 0) {
+                Row4 work = {0.f, 0.f, 0.f, 0.f};
+                {
+                    const float f = dot128_refblas(x0, cpos, quirk);
+                    if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+                        const float g = __fmul_rn(__fmul_rn(1.f - lut[lut_index(f)], lr), lambda);
+                        fma_row4(work, g, cpos);
+                        fma_row4(cpos, g, x0);
+                    }
+                }
+#pragma unroll 1
+                for (int k = 0; k < NEG; k++) {
+                    const uint32_t tk = __shfl_sync(FULL, tq0, k);
+                    if (tk == wi0) continue;
+                    float *cp = ctx + (int64_t)tk * D;
+                    Row4 cc = ld_row4(cp, lane);
+                    const float f = dot128_refblas(x0, cc, quirk);
+                    if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
+                    const float g = __fmul_rn(__fmul_rn(0.f - lut[lut_index(f)], lr), lambda);
+                    fma_row4(work, g, cc);
+                    fma_row4(cc, g, x0);
+                    st_row4(cp, lane, cc);
+                }
+                nx.v0 = x0.v0 + work.v0; nx.v1 = x0.v1 + work.v1; nx.v2 = x0.v2 + work.v2; nx.v3 = x0.v3 + work.v3;
+                stage[s][0][lane] = make_float4(nx.v0, nx.v1, nx.v2, nx.v3);
+                if (last_of_centre) st_row4(ctx + (int64_t)wi0 * D, lane, cpos);
+            }
+            __syncthreads();  // barrier p: target-row stores of pair p visible, stage[s] complete
+            // ---- phase B: x + work, work accumulated in the reference's order (pyx:146, 149) ----
+            if (!serial) {
+                Row4 work = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int m = 0; m < NT; m++) {  // predicated, no branches: all shared loads issue together
+                    const bool on = used[s][m] != 0;
+                    const float g = gs[s][m];
+                    const float4 cc = stage[s][m][lane];  // stale data of an older pair when !on: not used
+                    work.v0 = on ? fmaf(g, cc.x, work.v0) : work.v0; work.v1 = on ? fmaf(g, cc.y, work.v1) : work.v1;
+                    work.v2 = on ? fmaf(g, cc.z, work.v2) : work.v2; work.v3 = on ? fmaf(g, cc.w, work.v3) : work.v3;
+                }
+                nx.v0 = x0.v0 + work.v0; nx.v1 = x0.v1 + work.v1; nx.v2 = x0.v2 + work.v2; nx.v3 = x0.v3 + work.v3;
+            } else {
+                const float4 q = stage[s][0][lane];
+                nx.v0 = q.x; nx.v1 = q.y; nx.v2 = q.z; nx.v3 = q.w;
+            }
+            if (r == 0) st_row4(node + (int64_t)wj0 * D, lane, nx);
+            if (!v1) break;
+            // ---- requests for pair p+2 (stores of pairs <= p are visible; pair p+1's are not) ----
+            bool hz2 = false;
+            if (v2) {
+                if (wj2 != wj0 && wj2 != wj1)  // otherwise forwarded from registers at the start of pair p+2
+                    cp_async16(&xring[r][pc][4 * lane], node + (int64_t)wj2 * D + 4 * lane);
+                if (r > 0) {
+                    const uint32_t tq1 = tring[r][(p + 1) & 7][lane];
+                    const uint32_t u2 = __shfl_sync(FULL, tring[r][(p + 2) & 7][lane], ks);
+                    hz2 = __any_sync(FULL, tq1 == u2) || u2 == wi1;
+                    if (!hz2) cp_async16(&cring[r][pc][4 * lane], ctx + (int64_t)u2 * D + 4 * lane);
+                }
+            }
+            cp_async_commit();  // exactly one group per pair (possibly empty), samples of pair p+4 included
+            // ---- rotate ----
+            newc = last_of_centre;
+            hz0 = hz1; hz1 = hz2;
+            nx2 = nx1; nx1 = nx;
+            wjm2 = wjm1; wjm1 = wj0;
+            i0 = i1; j0 = j1; wi0 = wi1; wj0 = wj1;
+            i1 = i2; j1 = j2; wi1 = wi2; wj1 = wj2; v1 = v2;
+            s ^= 1;
+            p3 = p3 == 2 ? 0 : p3 + 1;
+        }
+        cp_async_commit();   // the sample request of the last iteration
+        cp_async_wait<0>();  // nothing of this walk may land in the rings after the next walk starts using them
+    }
+    if (n_tokens && threadIdx.x == 0) *n_tokens += tokens;
+}
+
 // ---- o1 ORDERED, size == 128, register-resident (same arithmetic as pair_o1 / dot_refblas, see o2_ordered_d128_kernel) -
 template <int NEG>
 __global__ void __launch_bounds__(32)
@@ -370,6 +796,120 @@ __global__ void __launch_bounds__(32)
             if (tb[k] == e0) cb[k] = r0;  // pyx:447 sees the updated row e0, also as a sample
         r1 = directed(r1, r0, e0, tb, cb);
         st_row4(node + (int64_t)e1 * D, lane, r1);
+    }
+}
+
+// ---- o1 ORDERED, size == 128, register-resident and software-pipelined (see o2_ordered_d128_pipe_kernel) -------------------
+// The 2+2*NEG rows of edge q+1 are requested before edge q is computed, the samples of edge q+2 before that.  Edge q
+// writes rows e0 and e1 only; a prefetched row with one of those indices is re-read after edge q's stores.
+template <int NEG>
+__global__ void __launch_bounds__(32)
+    o1_ordered_d128_pipe_kernel(float *node, const uint32_t *edges, int64_t n_edges, const uint64_t *seeds,
+                                uint64_t base_seed, Sampler S, float lr, bool quirk, const float *g_exp_table) {
+    constexpr int D = 128;
+    constexpr LcgJump<2 * NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < EXP_TABLE_SIZE; e += 32) lut[e] = g_exp_table[e];
+    __syncwarp();
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    auto directed = [&](const Row4 &x, const Row4 &target, uint32_t word_index, const uint32_t (&tt)[NEG],
+                        const Row4 (&c)[NEG]) -> Row4 {  // fast_o1, pyx:205-249
+        Row4 work = {0.f, 0.f, 0.f, 0.f};
+        {
+            const float f = dot128_refblas(x, target, quirk);
+            if (f > -MAX_EXP_F && f < MAX_EXP_F) fma_row4(work, __fmul_rn(1.f - lut[lut_index(f)], lr), target);
+        }
+        float f[NEG];
+#pragma unroll
+        for (int k = 0; k < NEG; k++) f[k] = dot128_refblas(x, c[k], quirk);
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            if (tt[k] == word_index) continue;                       // pyx:234-235
+            if (f[k] <= -MAX_EXP_F || f[k] >= MAX_EXP_F) continue;  // pyx:240-241
+            fma_row4(work, __fmul_rn(0.f - lut[lut_index(f[k])], lr), c[k]);  // pyx:243-245
+        }
+        const Row4 nx = {x.v0 + work.v0, x.v1 + work.v1, x.v2 + work.v2, x.v3 + work.v3};  // pyx:247
+        return nx;
+    };
+    auto sample = [&](int64_t q) -> uint32_t {  // the 2*NEG samples of edge q, one per lane
+        const uint64_t rnd = seeds ? seeds[q] : (splitmix64(base_seed ^ splitmix64((uint64_t)q)) & LCG_MASK);
+        return (lane < 2 * NEG) ? S.table[table_slot((myA * rnd + myC) & LCG_MASK, S.mod)] : 0u;
+    };
+    if (n_edges <= 0) return;
+    uint32_t e0 = edges[0], e1 = edges[1];
+    uint32_t tq_cur = sample(0);
+    uint32_t tq_nxt = n_edges > 1 ? sample(1) : 0u;
+    Row4 r0 = ld_row4(node + (int64_t)e0 * D, lane);
+    Row4 r1 = ld_row4(node + (int64_t)e1 * D, lane);
+    uint32_t ta[NEG], tb[NEG];
+    Row4 ca[NEG], cb[NEG];
+#pragma unroll
+    for (int k = 0; k < NEG; k++) {
+        ta[k] = __shfl_sync(FULL, tq_cur, k);
+        tb[k] = __shfl_sync(FULL, tq_cur, NEG + k);
+        ca[k] = ld_row4(node + (int64_t)ta[k] * D, lane);
+        cb[k] = ld_row4(node + (int64_t)tb[k] * D, lane);
+    }
+    for (int64_t q = 0; q < n_edges; q++) {  // node_embeddings.py:70-71
+        const bool has_next = q + 1 < n_edges;
+        uint32_t ne0 = 0, ne1 = 0, tq_new = 0;
+        uint32_t tna[NEG], tnb[NEG];
+        Row4 nr0 = r0, nr1 = r1;
+        Row4 nca[NEG], ncb[NEG];
+        bool stale = false;
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            tna[k] = __shfl_sync(FULL, tq_nxt, k);
+            tnb[k] = __shfl_sync(FULL, tq_nxt, NEG + k);
+            nca[k] = ca[k];
+            ncb[k] = cb[k];
+        }
+        if (has_next) {
+            ne0 = edges[2 * q + 2];
+            ne1 = edges[2 * q + 3];
+            if (q + 2 < n_edges) tq_new = sample(q + 2);
+            nr0 = ld_row4(node + (int64_t)ne0 * D, lane);
+            nr1 = ld_row4(node + (int64_t)ne1 * D, lane);
+            stale = ne0 == e0 || ne0 == e1 || ne1 == e0 || ne1 == e1;
+#pragma unroll
+            for (int k = 0; k < NEG; k++) {
+                nca[k] = ld_row4(node + (int64_t)tna[k] * D, lane);
+                ncb[k] = ld_row4(node + (int64_t)tnb[k] * D, lane);
+                stale = stale || tna[k] == e0 || tna[k] == e1 || tnb[k] == e0 || tnb[k] == e1;
+            }
+        }
+        // ---- edge q ----
+        r0 = directed(r0, r1, e1, ta, ca);  // pyx:444 (targets are read-only: a sample equal to e0 is the old row)
+        st_row4(node + (int64_t)e0 * D, lane, r0);
+        if (e1 == e0) r1 = r0;
+#pragma unroll
+        for (int k = 0; k < NEG; k++)
+            if (tb[k] == e0) cb[k] = r0;  // pyx:447 sees the updated row e0, also as a sample
+        r1 = directed(r1, r0, e0, tb, cb);
+        st_row4(node + (int64_t)e1 * D, lane, r1);
+        if (!has_next) break;
+        if (stale) {  // re-read after this edge's stores
+            nr0 = ld_row4(node + (int64_t)ne0 * D, lane);
+            nr1 = ld_row4(node + (int64_t)ne1 * D, lane);
+#pragma unroll
+            for (int k = 0; k < NEG; k++) {
+                nca[k] = ld_row4(node + (int64_t)tna[k] * D, lane);
+                ncb[k] = ld_row4(node + (int64_t)tnb[k] * D, lane);
+            }
+        }
+        e0 = ne0; e1 = ne1; r0 = nr0; r1 = nr1;
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            ta[k] = tna[k]; tb[k] = tnb[k]; ca[k] = nca[k]; cb[k] = ncb[k];
+        }
+        tq_nxt = tq_new;
     }
 }
 
@@ -556,10 +1096,41 @@ __global__ void __launch_bounds__(32)
 }  // namespace
 
 // ---- launchers (called from capi.cu) -------------------------------------------------------------------------------------
-int launch_o2_ordered(float *node, float *ctx, int size, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
-                      const uint64_t *seeds, uint64_t base_seed, const uint32_t *table, uint64_t table_len, int window,
-                      int negative, float lr, float lambda, bool quirk, int64_t *n_tokens, cudaStream_t st) {
+int launch_o2_ordered(float *node, float *ctx, int64_t n_rows, int size, const uint32_t *walks, const int64_t *walk_off,
+                      int64_t n_walks, const uint64_t *seeds, uint64_t base_seed, const uint32_t *table,
+                      uint64_t table_len, int window, int negative, float lr, float lambda, bool quirk, int64_t *n_tokens,
+                      cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
+    const bool disjoint = node + n_rows * size <= ctx || ctx + n_rows * size <= node;
+    if (size == 128 && !g_force_generic_ordered && disjoint && g_ordered_variant == 0) {  // warp per target row, same bits
+        switch (negative) {
+#define COMEMB_CASE(N)                                                                                             \
+    case N:                                                                                                        \
+        CUDA_TRY(cudaFuncSetAttribute(o2_ordered_d128_team_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      MAX_SENTENCE_LEN * 4));                                                      \
+        o2_ordered_d128_team_kernel<N><<<1, 32 * (N + 1), MAX_SENTENCE_LEN * 4, st>>>(node, ctx, walks, walk_off, n_walks, seeds, \
+                                                                   base_seed, S, window, lr, lambda, quirk,        \
+                                                                   n_tokens, comemb_lut_device());                 \
+        return (int)cudaGetLastError();
+            COMEMB_CASE(1) COMEMB_CASE(2) COMEMB_CASE(3) COMEMB_CASE(4) COMEMB_CASE(5) COMEMB_CASE(6) COMEMB_CASE(7)
+#undef COMEMB_CASE
+            default: break;
+        }
+    }
+    if (size == 128 && !g_force_generic_ordered && disjoint && g_ordered_variant != 8) {  // pipelined single warp
+        switch (negative) {
+#define COMEMB_CASE(N)                                                                                             \
+    case N:                                                                                                        \
+        CUDA_TRY(cudaFuncSetAttribute(o2_ordered_d128_pipe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      MAX_SENTENCE_LEN * 4));                                                      \
+        o2_ordered_d128_pipe_kernel<N><<<1, 32, MAX_SENTENCE_LEN * 4, st>>>(node, ctx, walks, walk_off, n_walks, seeds, base_seed, S, \
+                                                         window, lr, lambda, quirk, n_tokens, comemb_lut_device()); \
+        return (int)cudaGetLastError();
+            COMEMB_CASE(1) COMEMB_CASE(2) COMEMB_CASE(3) COMEMB_CASE(4) COMEMB_CASE(5) COMEMB_CASE(6) COMEMB_CASE(7)
+#undef COMEMB_CASE
+            default: break;
+        }
+    }
     if (size == 128 && !g_force_generic_ordered) {  // register-resident fast path, same bits
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                             \
@@ -584,6 +1155,18 @@ int launch_o1_ordered(float *node, int size, const uint32_t *edges, int64_t n_ed
                       uint64_t base_seed, const uint32_t *table, uint64_t table_len, int negative, float lr, bool quirk,
                       cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
+    if (size == 128 && !g_force_generic_ordered && g_ordered_variant != 8) {  // pipelined fast path, same bits
+        switch (negative) {
+#define COMEMB_CASE(N)                                                                                              \
+    case N:                                                                                                         \
+        o1_ordered_d128_pipe_kernel<N><<<1, 32, 0, st>>>(node, edges, n_edges, seeds, base_seed, S, lr, quirk,      \
+                                                         comemb_lut_device());                                      \
+        return (int)cudaGetLastError();
+            COMEMB_CASE(1) COMEMB_CASE(2) COMEMB_CASE(3) COMEMB_CASE(4) COMEMB_CASE(5) COMEMB_CASE(6) COMEMB_CASE(7)
+#undef COMEMB_CASE
+            default: break;
+        }
+    }
     if (size == 128 && !g_force_generic_ordered) {  // register-resident fast path, same bits
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                              \

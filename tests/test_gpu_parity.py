@@ -76,6 +76,50 @@ def test_o2_ordered_generic_kernel_at_d128(K, golden, name):
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
 
 
+@pytest.mark.parametrize("variant", [0, 700, 800])
+@pytest.mark.parametrize("N,neg,none_every", [(6, 5, 0), (12, 7, 5), (40, 3, 0), (40, 1, 3), (3000, 5, 0), (3000, 2, 7)])
+def test_o2_ordered_d128_kernel_variants_hazards(K, variant, N, neg, none_every):
+    """The three size-128 ORDERED kernels (0: one warp per target row with two-pair look-ahead, 7: single warp software
+    pipelined, 8: single warp plain) against the oracle, bit for bit, on inputs that hit every hazard path: tiny tables
+    (equal samples inside a pair -> serial path; samples equal to rows of the pairs in flight -> re-read; repeated walk
+    tokens -> register forwarding), None tokens, ragged and empty walks, and a table large enough for the clean path."""
+    from comemb_b200 import _lib
+    c = dict(cases.O2_CASES["o2_d128_small"], N=N, neg=neg, nw=12, L=30, W=4, seed=7000 + N + neg, ragged=True)
+    if none_every:
+        c["none_every"] = none_every
+    node, ctx, table, walks = cases.o2_inputs(c)
+    walks = list(walks) + [np.zeros(0, np.uint32), walks[0][:1], walks[1][:2]]
+    flat, off = cases.flatten_walks(walks)
+    seeds = O.seeds_from_numpy(np.random.RandomState(5), len(walks))
+    dn, dc = dev(node), dev(ctx)
+    _lib.check(_lib.load().comemb_set_tuning(0, 0, variant))
+    try:
+        K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), c["lr"], neg, c["W"], dev(table), mode=K.MODE_ORDERED)
+    finally:
+        _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
+    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], neg, c["W"], table, 1.0, O.DOT_REFBLAS_QUIRK)
+    assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+
+
+@pytest.mark.parametrize("variant", [0, 800])
+@pytest.mark.parametrize("N,neg", [(4, 5), (12, 7), (40, 3), (3000, 5)])
+def test_o1_ordered_d128_kernel_variants_hazards(K, variant, N, neg):
+    """Pipelined (0) and plain (8) size-128 ORDERED o1 kernels vs the oracle, bit for bit: self loops, repeated
+    endpoints in consecutive edges and samples that hit the previous edge's rows (tiny tables)."""
+    from comemb_b200 import _lib
+    c = dict(cases.O1_CASES["o1_d128"], N=N, neg=neg, E=150, seed=7100 + N + neg, selfloop_every=11)
+    node, table, edges = cases.o1_inputs(c)
+    seeds = O.seeds_from_numpy(np.random.RandomState(6), len(edges))
+    dn = dev(node)
+    _lib.check(_lib.load().comemb_set_tuning(0, 0, variant))
+    try:
+        K.o1_batch(dn, dev(edges), dev(seeds), c["lr"], neg, dev(table), mode=K.MODE_ORDERED)
+    finally:
+        _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
+    O.o1_edges(node, edges, seeds, c["lr"], neg, table, O.DOT_REFBLAS_QUIRK)
+    assert np.array_equal(host(dn), node)
+
+
 @pytest.mark.parametrize("name", ["o1_d128", "o1_d128_init_like_model"])
 def test_o1_ordered_generic_kernel_at_d128(K, golden, name):
     from comemb_b200 import _lib
