@@ -491,25 +491,26 @@ __global__ void __launch_bounds__(32)
     if (n_tokens && lane == 0) *n_tokens += tokens;
 }
 
-// ---- o2 ORDERED, size == 128: one warp PER TARGET ROW of a pair (NEG+1 warps), still strictly sequential over pairs -------
+// ---- o2 ORDERED, size == 128: one warp PER TARGET ROW of a pair + a scheduling warp; strictly sequential over pairs ---------
 // A single warp replaying the stream is bound by instruction latency (about 570 dependent-ish instructions per pair, no
-// other warp to hide them).  The NEG+1 targets of one pair are independent of each other unless two samples coincide,
-// so warp 0 owns the centre's context row (registers, across the window) and warp r>0 owns sample r-1: phase A (all
-// warps in parallel) dot -> sigma -> g, publish (g, old target row) in shared memory, update + store the target row;
-// one CTA barrier; phase B (every warp, redundantly, so that each has the new node row for forwarding) accumulates
-// `work` in the reference's order d = 0..NEG and forms x + work; warp 0 stores it.
-// Rows are requested two pairs ahead and samples four pairs ahead with cp.async into per-warp shared-memory rings
-// (register prefetch does not work at this depth: the load scoreboard is a counter, so touching the oldest request
-// waits for the youngest).  A request for pair p+2 is issued after barrier p, which makes the stores of pairs <= p
-// visible; a requested row that pair p+1 writes is re-read at the start of pair p+2 (hazard flag), node rows of the two
-// pairs in flight are forwarded from registers.  A pair with two equal samples is executed by warp 0 alone, one target
-// after the other.  Every floating-point operation and its order is the one of o2_ordered_d128_kernel: same bits.
+// other warp to hide them).  Two things are taken off that chain:
+//  * Everything that does not depend on the embeddings -- the order of the (centre, context) pairs, the LCG stream, the
+//    sampler-table look-ups, and which rows of neighbouring pairs coincide -- is produced by a SCHEDULING warp, 32 pairs
+//    at a time (one pair per lane), two chunks ahead of the workers, into a shared-memory ring of pair descriptors.
+//  * The NEG+1 targets of one pair are independent of each other unless two samples coincide, so worker warp 0 owns the
+//    centre's context row (registers, across the window) and worker r>0 owns sample r-1: phase A (all workers in
+//    parallel) dot -> sigma -> g, publish (g, old target row) in shared memory, update + store the target row; one
+//    barrier among the workers; phase B (every worker, redundantly, so that each has the new node row for forwarding)
+//    accumulates `work` in the reference's order d = 0..NEG and forms x + work; worker 0 stores it.
+// Rows are requested two pairs ahead with cp.async into per-warp shared-memory rings (register prefetch does not work
+// at this depth: the load scoreboard is a counter, so touching the oldest request waits for the youngest).  A request
+// for pair p+2 is issued after barrier p, which makes the stores of pairs <= p visible; a row that pair p+1 writes is
+// not requested but read at the start of pair p+2 (hazard bit in the descriptor), node rows of the two pairs in flight
+// are forwarded from registers.  A pair with two equal samples is executed by worker 0 alone, one target after the
+// other.  Every floating-point operation and its order is the one of o2_ordered_d128_kernel: same bits.
+// Requires window <= 15 (a centre's window fits the 32 lanes of the scheduling warp) and disjoint node / ctx tables.
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -517,224 +518,285 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+template <int ID, int NTHREADS>
+__device__ __forceinline__ void named_barrier() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory");
+}
 __device__ __forceinline__ Row4 lds_row4(const float *row, int lane) {
     Row4 v;
     v.v0 = row[lane]; v.v1 = row[lane + 32]; v.v2 = row[lane + 64]; v.v3 = row[lane + 96];
     return v;
 }
 
+constexpr uint32_t PD_VALID = 1u, PD_SERIAL = 2u, PD_LAST = 4u, PD_NEWC = 8u;  // pair descriptor flags
+constexpr int PD_XSRC_SHIFT = 4;  // 2 bits: 0 = node row from the ring, 1 / 2 = x + work of pair p-1 / p-2
+constexpr int PD_HZ_SHIFT = 8;    // bit 8+k: sample k's row is written by pair p-1 -> read it at the start of pair p
+constexpr int TEAM_MAX_WINDOW = 15;
+
 template <int NEG>
-__global__ void __launch_bounds__(32 * (NEG + 1), 1)
+__global__ void __launch_bounds__(32 * (NEG + 2), 1)
     o2_ordered_d128_team_kernel(float *node, float *ctx, const uint32_t *walks, const int64_t *walk_off,
                                 int64_t n_walks, const uint64_t *seeds, uint64_t base_seed, Sampler S, int window,
                                 float lr, float lambda, bool quirk, int64_t *n_tokens, const float *g_exp_table) {
     constexpr int D = 128;
-    constexpr int NT = NEG + 1;
-    constexpr LcgJump<NEG> J{};
+    constexpr int NT = NEG + 1;          // worker warps
+    constexpr int NALL = 32 * (NT + 1);  // + the scheduling warp
     __shared__ float lut[EXP_TABLE_SIZE];
     __shared__ float4 stage[2][NT][32];  // old target rows of the pair (Row4 layout), or x + work in serial mode
-    __shared__ float gs[2][NT];
-    __shared__ int used[2][NT];
-    __shared__ __align__(16) float xring[NT][3][D];  // per warp: node row of pairs p, p+1, p+2
-    __shared__ __align__(16) float cring[NT][3][D];  // per warp: own sample row of pairs p, p+1, p+2
-    __shared__ uint32_t tring[NT][8][32];            // per warp: samples of pairs p .. p+4 (lane k = sample k)
-    extern __shared__ uint32_t path[];               // [MAX_SENTENCE_LEN] tokens of the current walk
+    __shared__ __align__(16) float gs[2][8];   // g of target d (padded to 8: two 128-bit reads)
+    __shared__ __align__(16) int used[2][8];   // target d took part (pyx:135-136, 141-142)
+    __shared__ __align__(16) float xring[NT][3][D];  // per worker: node row of pairs p, p+1, p+2
+    __shared__ __align__(16) float cring[NT][3][D];  // per worker: own sample row of pairs p, p+1, p+2
+    // pair descriptors, ring of 3 chunks x 32 pairs, index q = 32 * chunk + slot
+    __shared__ __align__(16) uint4 d_hdr[96];       // {flags, wi (centre row), wj (context row), -}
+    __shared__ __align__(16) uint32_t d_t[96][8];   // the NEG samples of the pair
+    __shared__ uint64_t JA[33], JC[33];  // LCG jump by NEG*k steps
     const int lane = threadIdx.x & 31;
     const int r = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += 32 * NT) lut[e] = g_exp_table[e];
-    for (int q = 0; q < 8; q++) tring[r][q][lane] = COMEMB_TOKEN_NONE;  // lanes >= NEG keep a value no row has
-    __syncthreads();
-    uint64_t myA = 1, myC = 0;
-#pragma unroll
-    for (int k = 0; k < NEG; k++)
-        if (lane == k) {
-            myA = J.A[k];
-            myC = J.C[k];
-        }
-    const int ks = r > 0 ? r - 1 : 0;  // own target row: warp 0 -> ctx[wi] (cpos), warp r -> ctx[sample r-1]
-    int64_t tokens = 0;
-    for (int64_t w = 0; w < n_walks; w++) {
-        const int len = (int)min((int64_t)MAX_SENTENCE_LEN, walk_off[w + 1] - walk_off[w]);
-        __syncthreads();  // every store of the previous walk is visible; `path`, rings and stages are free
-        {
-            const uint32_t *gpath = walks + walk_off[w];
-            for (int e = threadIdx.x; e < len; e += 32 * NT) path[e] = gpath[e];
-        }
-        __syncthreads();
-        if (r == 0) {
-            int cnt = 0;
-            for (int e = lane; e < len; e += 32) cnt += (path[e] != COMEMB_TOKEN_NONE);
-            tokens += __reduce_add_sync(FULL, cnt);
-        }
-        uint64_t rnd = seeds ? seeds[w] : (splitmix64(base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
-        auto request_samples = [&](int q) {  // samples of pair q -> tring[.][q & 7] (pyx:133-134)
-            if (lane < NEG) cp_async4(&tring[r][q & 7][lane], S.table + table_slot((myA * rnd + myC) & LCG_MASK, S.mod));
-            rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
-        };
-        auto seek = [&](int &i, int &j, uint32_t &wi, uint32_t &wj) -> bool {  // pyx:494-507
-            while (i < len) {
-                if (wi != COMEMB_TOKEN_NONE) {
-                    const int j1 = min(len, i + window + 1);
-                    for (; j < j1; j++) {
-                        if (j == i) continue;
-                        wj = path[j];
-                        if (wj != COMEMB_TOKEN_NONE) return true;
-                    }
-                }
-                i++;
-                if (i < len) {
-                    wi = path[i];
-                    j = max(0, i - window);
-                }
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += NALL) lut[e] = g_exp_table[e];
+
+    if (r == NT) {
+        // =========================== scheduling warp ===========================
+        for (int k = lane; k < 33; k += 32) {
+            uint64_t A = 1, C = 0;
+            for (int q = 0; q < NEG * k; q++) {
+                C = (C * LCG_MUL + 11ULL) & LCG_MASK;
+                A = (A * LCG_MUL) & LCG_MASK;
             }
-            return false;
-        };
-        // pairs p (0), p+1 (1), p+2 (2)
-        int i0 = 0, j0 = 0;
-        uint32_t wi0 = len > 0 ? path[0] : COMEMB_TOKEN_NONE, wj0 = 0;
-        if (!seek(i0, j0, wi0, wj0)) continue;
-        int i1 = i0, j1 = j0 + 1;
-        uint32_t wi1 = wi0, wj1 = 0;
-        bool v1 = seek(i1, j1, wi1, wj1);
-        // prologue: samples of pairs 0..3, then the rows of pairs 0 and 1 (one cp.async group each)
-        request_samples(0); request_samples(1); request_samples(2); request_samples(3);
-        cp_async_commit();
-        cp_async_wait<0>();
+            JA[k] = A;
+            JC[k] = C;
+        }
         __syncwarp();
-        cp_async16(&xring[r][0][4 * lane], node + (int64_t)wj0 * D + 4 * lane);
-        if (r > 0) cp_async16(&cring[r][0][4 * lane], ctx + (int64_t)__shfl_sync(FULL, tring[r][0][lane], ks) * D + 4 * lane);
-        cp_async_commit();
-        if (v1) cp_async16(&xring[r][1][4 * lane], node + (int64_t)wj1 * D + 4 * lane);
-        cp_async_commit();
-        bool hz0 = false;
-        bool hz1 = true;     // pair 1's sample row is read at its start (after barrier 0); once per walk
-        bool newc = true;    // warp 0: read the centre's context row at the start of the pair
-        Row4 cpos = {0.f, 0.f, 0.f, 0.f};
-        Row4 nx1 = cpos, nx2 = cpos;                       // x + work of pairs p-1, p-2
-        uint32_t wjm1 = COMEMB_TOKEN_NONE, wjm2 = COMEMB_TOKEN_NONE;  // their rows
-        int s = 0, p3 = 0;  // p3 = p mod 3
-        for (int p = 0;; p++) {
-            const int pc = p3 == 0 ? 2 : p3 - 1;  // (p + 2) mod 3
-            // ---- start of pair p: its requests have landed (at most the youngest group may be pending) ----
-            cp_async_wait<1>();
+        int64_t w = -1, tokens = 0;
+        const uint32_t *gpath = walks;
+        int len = 0, i = 0, j_base = 0;
+        uint64_t rnd_cur = 0;
+        uint32_t wi_cur = COMEMB_TOKEN_NONE, pending = 0, full = 0;
+        bool ended = false;
+        int end_chunk = -1;
+        auto produce = [&](int c) {
+            const int buf = c % 3, q0 = 32 * buf, qprev = 32 * ((buf + 2) % 3);
+            d_hdr[q0 + lane].x = 0u;
             __syncwarp();
-            const uint32_t tq0 = tring[r][p & 7][lane];
-            const uint32_t u0 = __shfl_sync(FULL, tq0, ks);
-            Row4 x0;
-            if (wj0 == wjm1) x0 = nx1;
-            else if (wj0 == wjm2) x0 = nx2;
-            else x0 = lds_row4(xring[r][p3], lane);
-            Row4 c0;
-            if (r == 0) {
-                if (newc) cpos = ld_row4(ctx + (int64_t)wi0 * D, lane);  // after barrier p-1: everything visible
-                c0 = cpos;
-            } else {
-                if (hz0) c0 = ld_row4(ctx + (int64_t)u0 * D, lane);
-                else c0 = lds_row4(cring[r][p3], lane);
+            int filled = 0;
+            while (filled < 32 && !ended) {
+                if (pending == 0u) {  // next centre (pyx:494-501)
+                    i++;
+                    while (i >= len) {
+                        w++;
+                        if (w >= n_walks) {
+                            ended = true;
+                            break;
+                        }
+                        gpath = walks + walk_off[w];
+                        len = (int)min((int64_t)MAX_SENTENCE_LEN, walk_off[w + 1] - walk_off[w]);
+                        rnd_cur = seeds ? seeds[w] : (splitmix64(base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+                        i = 0;
+                    }
+                    if (ended) break;
+                    wi_cur = gpath[i];
+                    if (wi_cur == COMEMB_TOKEN_NONE) continue;
+                    tokens++;
+                    j_base = max(0, i - window);
+                    const int jj = j_base + lane;
+                    const bool ok = jj < min(len, i + window + 1) && jj != i && gpath[jj] != COMEMB_TOKEN_NONE;
+                    full = __ballot_sync(FULL, ok);  // pyx:503-507: the centre's valid contexts, in order
+                    pending = full;
+                    if (full == 0u) continue;
+                }
+                const int take = min(__popc(pending), 32 - filled);
+                const int rank = __popc(pending & ((1u << lane) - 1u));
+                const bool mine = ((pending >> lane) & 1u) && rank < take;
+                if (mine) {  // this lane emits pair `filled + rank`: context position j_base + lane
+                    const int slot = filled + rank;
+                    const uint32_t wj = gpath[j_base + lane];
+                    uint32_t fl = PD_VALID;
+                    if (lane == __ffs(full) - 1) fl |= PD_NEWC;
+                    if (lane == 31 - __clz(full)) fl |= PD_LAST;
+                    uint64_t rr = (JA[rank] * rnd_cur + JC[rank]) & LCG_MASK;  // pair's position in the walk's stream
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) {  // pyx:133-134
+                        d_t[q0 + slot][k] = S.table[table_slot(rr, S.mod)];
+                        rr = lcg_next(rr);
+                    }
+                    d_hdr[q0 + slot] = make_uint4(fl, wi_cur, wj, 0u);
+                }
+                rnd_cur = (JA[take] * rnd_cur + JC[take]) & LCG_MASK;
+                pending &= ~__ballot_sync(FULL, mine);
+                filled += take;
             }
-            // ---- look ahead: position of pair p+2, samples of pair p+4 ----
-            int i2 = i1, j2 = j1 + 1;
-            uint32_t wi2 = wi1, wj2 = 0;
-            const bool v2 = v1 && seek(i2, j2, wi2, wj2);
-            request_samples(p + 4);
-            const bool last_of_centre = !v1 || i1 != i0;
-            // two equal samples inside this pair -> serial execution by warp 0
-            const unsigned eq = __match_any_sync(FULL, tq0);
-            const bool serial = __any_sync(FULL, lane < NEG && (eq & ((1u << lane) - 1u)) != 0u);
-            // ---- phase A ----
-            Row4 nx;
-            if (!serial) {
-                bool use = !(r > 0 && u0 == wi0);  // pyx:135-136
-                float g = 0.f;
-                if (use) {
-                    const float f = dot128_refblas(x0, c0, quirk);
-                    use = f > -MAX_EXP_F && f < MAX_EXP_F;  // pyx:141-142
-                    if (use) g = __fmul_rn(__fmul_rn((r == 0 ? 1.f : 0.f) - lut[lut_index(f)], lr), lambda);
-                }
-                if (lane == 0) {
-                    gs[s][r] = g;
-                    used[s][r] = use ? 1 : 0;
-                }
-                if (use) {
-                    stage[s][r][lane] = make_float4(c0.v0, c0.v1, c0.v2, c0.v3);
-                    fma_row4(c0, g, x0);  // pyx:147
-                    if (r > 0) st_row4(ctx + (int64_t)u0 * D, lane, c0);
-                    else cpos = c0;
-                }
-                if (r == 0 && last_of_centre) st_row4(ctx + (int64_t)wi0 * D, lane, cpos);
-            } else if (r == 0) {
-                Row4 work = {0.f, 0.f, 0.f, 0.f};
-                {
-                    const float f = dot128_refblas(x0, cpos, quirk);
-                    if (f > -MAX_EXP_F && f < MAX_EXP_F) {
-                        const float g = __fmul_rn(__fmul_rn(1.f - lut[lut_index(f)], lr), lambda);
-                        fma_row4(work, g, cpos);
-                        fma_row4(cpos, g, x0);
+            if (ended && end_chunk < 0) end_chunk = c;  // this chunk holds the end marker (a descriptor without PD_VALID)
+            __syncwarp();
+            // relations with the two previous pairs (lane = slot)
+            uint32_t fl = d_hdr[q0 + lane].x;
+            if (fl & PD_VALID) {
+                const int q1 = lane >= 1 ? q0 + lane - 1 : qprev + 31;      // pair p-1
+                const int q2 = lane >= 2 ? q0 + lane - 2 : qprev + 30 + lane;  // pair p-2
+                const bool has1 = c > 0 || lane >= 1, has2 = c > 0 || lane >= 2;
+                uint32_t t[NEG];
+#pragma unroll
+                for (int k = 0; k < NEG; k++) t[k] = d_t[q0 + lane][k];
+                bool dup = false;
+#pragma unroll
+                for (int k = 1; k < NEG; k++)
+#pragma unroll
+                    for (int q = 0; q < k; q++) dup = dup || (t[q] == t[k]);
+                if (dup) fl |= PD_SERIAL;
+                const uint32_t wj = d_hdr[q0 + lane].z;
+                if (has1 && wj == d_hdr[q1].z) fl |= 1u << PD_XSRC_SHIFT;
+                else if (has2 && wj == d_hdr[q2].z) fl |= 2u << PD_XSRC_SHIFT;
+                if (has1) {
+                    const uint32_t pwi = d_hdr[q1].y;
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) {
+                        bool hz = t[k] == pwi;  // the previous pair may end its centre and store that row
+#pragma unroll
+                        for (int q = 0; q < NEG; q++) hz = hz || (t[k] == d_t[q1][q]);
+                        if (hz) fl |= 1u << (PD_HZ_SHIFT + k);
                     }
                 }
-#pragma unroll 1
-                for (int k = 0; k < NEG; k++) {
-                    const uint32_t tk = __shfl_sync(FULL, tq0, k);
-                    if (tk == wi0) continue;
-                    float *cp = ctx + (int64_t)tk * D;
-                    Row4 cc = ld_row4(cp, lane);
-                    const float f = dot128_refblas(x0, cc, quirk);
-                    if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
-                    const float g = __fmul_rn(__fmul_rn(0.f - lut[lut_index(f)], lr), lambda);
-                    fma_row4(work, g, cc);
-                    fma_row4(cc, g, x0);
-                    st_row4(cp, lane, cc);
-                }
-                nx.v0 = x0.v0 + work.v0; nx.v1 = x0.v1 + work.v1; nx.v2 = x0.v2 + work.v2; nx.v3 = x0.v3 + work.v3;
-                stage[s][0][lane] = make_float4(nx.v0, nx.v1, nx.v2, nx.v3);
-                if (last_of_centre) st_row4(ctx + (int64_t)wi0 * D, lane, cpos);
+                d_hdr[q0 + lane].x = fl;
             }
-            __syncthreads();  // barrier p: target-row stores of pair p visible, stage[s] complete
-            // ---- phase B: x + work, work accumulated in the reference's order (pyx:146, 149) ----
-            if (!serial) {
-                Row4 work = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int m = 0; m < NT; m++) {  // predicated, no branches: all shared loads issue together
-                    const bool on = used[s][m] != 0;
-                    const float g = gs[s][m];
-                    const float4 cc = stage[s][m][lane];  // stale data of an older pair when !on: not used
-                    work.v0 = on ? fmaf(g, cc.x, work.v0) : work.v0; work.v1 = on ? fmaf(g, cc.y, work.v1) : work.v1;
-                    work.v2 = on ? fmaf(g, cc.z, work.v2) : work.v2; work.v3 = on ? fmaf(g, cc.w, work.v3) : work.v3;
-                }
-                nx.v0 = x0.v0 + work.v0; nx.v1 = x0.v1 + work.v1; nx.v2 = x0.v2 + work.v2; nx.v3 = x0.v3 + work.v3;
-            } else {
-                const float4 q = stage[s][0][lane];
-                nx.v0 = q.x; nx.v1 = q.y; nx.v2 = q.z; nx.v3 = q.w;
-            }
-            if (r == 0) st_row4(node + (int64_t)wj0 * D, lane, nx);
-            if (!v1) break;
-            // ---- requests for pair p+2 (stores of pairs <= p are visible; pair p+1's are not) ----
-            bool hz2 = false;
-            if (v2) {
-                if (wj2 != wj0 && wj2 != wj1)  // otherwise forwarded from registers at the start of pair p+2
-                    cp_async16(&xring[r][pc][4 * lane], node + (int64_t)wj2 * D + 4 * lane);
-                if (r > 0) {
-                    const uint32_t tq1 = tring[r][(p + 1) & 7][lane];
-                    const uint32_t u2 = __shfl_sync(FULL, tring[r][(p + 2) & 7][lane], ks);
-                    hz2 = __any_sync(FULL, tq1 == u2) || u2 == wi1;
-                    if (!hz2) cp_async16(&cring[r][pc][4 * lane], ctx + (int64_t)u2 * D + 4 * lane);
-                }
-            }
-            cp_async_commit();  // exactly one group per pair (possibly empty), samples of pair p+4 included
-            // ---- rotate ----
-            newc = last_of_centre;
-            hz0 = hz1; hz1 = hz2;
-            nx2 = nx1; nx1 = nx;
-            wjm2 = wjm1; wjm1 = wj0;
-            i0 = i1; j0 = j1; wi0 = wi1; wj0 = wj1;
-            i1 = i2; j1 = j2; wi1 = wi2; wj1 = wj2; v1 = v2;
-            s ^= 1;
-            p3 = p3 == 2 ? 0 : p3 + 1;
+            __syncwarp();
+        };
+        i = 0; len = 0; i = -1;  // so that the first `i++ ... i >= len` opens walk 0
+        produce(0);
+        produce(1);
+        named_barrier<0, NALL>();  // chunks 0 and 1 are ready
+        for (int c = 0;; c++) {     // workers are in chunk c
+            if (end_chunk >= 0 && end_chunk <= c) break;  // they stop inside this chunk: no further chunk barrier
+            produce(c + 2);
+            named_barrier<0, NALL>();  // workers move from chunk c to c+1
         }
-        cp_async_commit();   // the sample request of the last iteration
-        cp_async_wait<0>();  // nothing of this walk may land in the rings after the next walk starts using them
+        if (n_tokens && lane == 0) *n_tokens += tokens;
+        return;
     }
-    if (n_tokens && threadIdx.x == 0) *n_tokens += tokens;
+
+    // =========================== worker warps ===========================
+    const int ks = r > 0 ? r - 1 : 0;  // own target row: worker 0 -> ctx[wi] (cpos), worker r -> ctx[sample r-1]
+    float *const xr = &xring[r][0][0], *const cr = &cring[r][0][0];
+    const float *const node_l = node + 4 * lane, *const ctx_l = ctx + 4 * lane;
+    auto request = [&](int q, int ring) {  // cp.async the rows of the pair described at q into ring slot `ring`
+        const uint4 h = d_hdr[q];
+        if (h.x & PD_VALID) {
+            if (((h.x >> PD_XSRC_SHIFT) & 3u) == 0u) cp_async16(xr + ring * D + 4 * lane, node_l + (int64_t)h.z * D);
+            if (r > 0 && !((h.x >> (PD_HZ_SHIFT + ks)) & 1u))
+                cp_async16(cr + ring * D + 4 * lane, ctx_l + (int64_t)d_t[q][ks] * D);
+        }
+        cp_async_commit();  // exactly one group per pair (possibly empty)
+    };
+    named_barrier<0, NALL>();  // chunks 0 and 1 are ready (also: lut is loaded)
+    request(0, 0);
+    request(1, 1);
+    Row4 cpos = {0.f, 0.f, 0.f, 0.f};
+    Row4 nx1 = cpos, nx2 = cpos;  // x + work of pairs p-1, p-2
+    int s = 0, p3 = 0, q = 0;  // q: descriptor index of pair p
+    for (;;) {
+        // ---- start of pair p: its requests have landed (at most the youngest group may be pending) ----
+        cp_async_wait<1>();
+        __syncwarp();
+        const uint4 hdr = d_hdr[q];
+        const uint32_t fl = hdr.x;
+        if (!(fl & PD_VALID)) break;
+        const uint32_t wi0 = hdr.y, wj0 = hdr.z, u0 = d_t[q][ks];
+        const uint32_t xsrc = (fl >> PD_XSRC_SHIFT) & 3u;
+        Row4 x0;
+        if (xsrc == 1u) x0 = nx1;
+        else if (xsrc == 2u) x0 = nx2;
+        else x0 = lds_row4(xr + p3 * D, lane);
+        Row4 c0;
+        if (r == 0) {
+            if (fl & PD_NEWC) cpos = ld_row4(ctx + (int64_t)wi0 * D, lane);  // after barrier p-1: everything visible
+            c0 = cpos;
+        } else {
+            if ((fl >> (PD_HZ_SHIFT + ks)) & 1u) c0 = ld_row4(ctx + (int64_t)u0 * D, lane);
+            else c0 = lds_row4(cr + p3 * D, lane);
+        }
+        const bool serial = (fl & PD_SERIAL) != 0u, last_of_centre = (fl & PD_LAST) != 0u;
+        // ---- phase A ----
+        Row4 nx;
+        if (!serial) {
+            bool use = !(r > 0 && u0 == wi0);  // pyx:135-136
+            float g = 0.f;
+            if (use) {
+                const float f = dot128_refblas(x0, c0, quirk);
+                use = f > -MAX_EXP_F && f < MAX_EXP_F;  // pyx:141-142
+                if (use) g = __fmul_rn(__fmul_rn((r == 0 ? 1.f : 0.f) - lut[lut_index(f)], lr), lambda);
+            }
+            if (lane == 0) {
+                gs[s][r] = g;
+                used[s][r] = use ? 1 : 0;
+            }
+            if (use) {
+                stage[s][r][lane] = make_float4(c0.v0, c0.v1, c0.v2, c0.v3);
+                fma_row4(c0, g, x0);  // pyx:147
+                if (r > 0) st_row4(ctx + (int64_t)u0 * D, lane, c0);
+                else cpos = c0;
+            }
+            if (r == 0 && last_of_centre) st_row4(ctx + (int64_t)wi0 * D, lane, cpos);
+        } else if (r == 0) {
+            Row4 work = {0.f, 0.f, 0.f, 0.f};
+            {
+                const float f = dot128_refblas(x0, cpos, quirk);
+                if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+                    const float g = __fmul_rn(__fmul_rn(1.f - lut[lut_index(f)], lr), lambda);
+                    fma_row4(work, g, cpos);
+                    fma_row4(cpos, g, x0);
+                }
+            }
+#pragma unroll 1
+            for (int k = 0; k < NEG; k++) {
+                const uint32_t tk = d_t[q][k];
+                if (tk == wi0) continue;
+                float *cp = ctx + (int64_t)tk * D;
+                Row4 cc = ld_row4(cp, lane);
+                const float f = dot128_refblas(x0, cc, quirk);
+                if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
+                const float g = __fmul_rn(__fmul_rn(0.f - lut[lut_index(f)], lr), lambda);
+                fma_row4(work, g, cc);
+                fma_row4(cc, g, x0);
+                st_row4(cp, lane, cc);
+            }
+            nx.v0 = x0.v0 + work.v0; nx.v1 = x0.v1 + work.v1; nx.v2 = x0.v2 + work.v2; nx.v3 = x0.v3 + work.v3;
+            stage[s][0][lane] = make_float4(nx.v0, nx.v1, nx.v2, nx.v3);
+            if (last_of_centre) st_row4(ctx + (int64_t)wi0 * D, lane, cpos);
+        }
+        named_barrier<1, 32 * NT>();  // barrier p: target-row stores of pair p visible, stage[s] complete
+        // ---- phase B: x + work, work accumulated in the reference's order (pyx:146, 149) ----
+        if (!serial) {
+            Row4 work = {0.f, 0.f, 0.f, 0.f};
+            int un[8];
+            float gn[8];
+            *(int4 *)&un[0] = *(const int4 *)&used[s][0];
+            *(float4 *)&gn[0] = *(const float4 *)&gs[s][0];
+            if (NT > 4) {
+                *(int4 *)&un[4] = *(const int4 *)&used[s][4];
+                *(float4 *)&gn[4] = *(const float4 *)&gs[s][4];
+            }
+#pragma unroll
+            for (int m = 0; m < NT; m++) {  // predicated, no branches: all shared loads issue together
+                const bool on = un[m] != 0;
+                const float g = gn[m];
+                const float4 cc = stage[s][m][lane];  // stale data of an older pair when !on: not used
+                work.v0 = on ? fmaf(g, cc.x, work.v0) : work.v0; work.v1 = on ? fmaf(g, cc.y, work.v1) : work.v1;
+                work.v2 = on ? fmaf(g, cc.z, work.v2) : work.v2; work.v3 = on ? fmaf(g, cc.w, work.v3) : work.v3;
+            }
+            nx.v0 = x0.v0 + work.v0; nx.v1 = x0.v1 + work.v1; nx.v2 = x0.v2 + work.v2; nx.v3 = x0.v3 + work.v3;
+        } else {
+            const float4 q = stage[s][0][lane];
+            nx.v0 = q.x; nx.v1 = q.y; nx.v2 = q.z; nx.v3 = q.w;
+        }
+        if (r == 0) st_row4(node + (int64_t)wj0 * D, lane, nx);
+        // ---- requests for pair p+2 (stores of pairs <= p are visible; pair p+1's are not) ----
+        request(q >= 94 ? q - 94 : q + 2, p3 == 0 ? 2 : p3 - 1);
+        // ---- rotate ----
+        nx2 = nx1; nx1 = nx;
+        s ^= 1;
+        p3 = p3 == 2 ? 0 : p3 + 1;
+        if ((q & 31) == 31) named_barrier<0, NALL>();  // the scheduling warp has finished chunk c+2; chunk c's buffer is free
+        q = q == 95 ? 0 : q + 1;
+    }
+    cp_async_wait<0>();
 }
 
 // ---- o1 ORDERED, size == 128, register-resident (same arithmetic as pair_o1 / dot_refblas, see o2_ordered_d128_kernel) -
@@ -1102,13 +1164,12 @@ int launch_o2_ordered(float *node, float *ctx, int64_t n_rows, int size, const u
                       cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
     const bool disjoint = node + n_rows * size <= ctx || ctx + n_rows * size <= node;
-    if (size == 128 && !g_force_generic_ordered && disjoint && g_ordered_variant == 0) {  // warp per target row, same bits
+    if (size == 128 && !g_force_generic_ordered && disjoint && g_ordered_variant == 0 &&
+        window <= TEAM_MAX_WINDOW) {  // warp per target row + scheduling warp, same bits
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                             \
     case N:                                                                                                        \
-        CUDA_TRY(cudaFuncSetAttribute(o2_ordered_d128_team_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      MAX_SENTENCE_LEN * 4));                                                      \
-        o2_ordered_d128_team_kernel<N><<<1, 32 * (N + 1), MAX_SENTENCE_LEN * 4, st>>>(node, ctx, walks, walk_off, n_walks, seeds, \
+        o2_ordered_d128_team_kernel<N><<<1, 32 * (N + 2), 0, st>>>(node, ctx, walks, walk_off, n_walks, seeds,     \
                                                                    base_seed, S, window, lr, lambda, quirk,        \
                                                                    n_tokens, comemb_lut_device());                 \
         return (int)cudaGetLastError();
