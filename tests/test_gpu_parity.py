@@ -77,14 +77,17 @@ def test_o2_ordered_generic_kernel_at_d128(K, golden, name):
 
 
 @pytest.mark.parametrize("variant", [0, 700, 800])
-@pytest.mark.parametrize("N,neg,none_every", [(6, 5, 0), (12, 7, 5), (40, 3, 0), (40, 1, 3), (3000, 5, 0), (3000, 2, 7)])
-def test_o2_ordered_d128_kernel_variants_hazards(K, variant, N, neg, none_every):
-    """The three size-128 ORDERED kernels (0: one warp per target row with two-pair look-ahead, 7: single warp software
-    pipelined, 8: single warp plain) against the oracle, bit for bit, on inputs that hit every hazard path: tiny tables
-    (equal samples inside a pair -> serial path; samples equal to rows of the pairs in flight -> re-read; repeated walk
-    tokens -> register forwarding), None tokens, ragged and empty walks, and a table large enough for the clean path."""
+@pytest.mark.parametrize("N,neg,none_every,W", [(6, 5, 0, 4), (12, 7, 5, 4), (40, 3, 0, 4), (40, 1, 3, 2), (3000, 5, 0, 10),
+                                                (3000, 2, 7, 15), (3000, 6, 0, 1), (40, 5, 0, 16), (3000, 5, 4, 20)])
+def test_o2_ordered_d128_kernel_variants_hazards(K, variant, N, neg, none_every, W):
+    """The three size-128 ORDERED kernels (0: scheduling warp + one worker warp per target row with two-pair look-ahead
+    -- window <= 15, wider windows take the pipelined kernel --, 7: single warp software pipelined, 8: single warp plain)
+    against the oracle, bit for bit, on inputs that hit every hazard path: tiny tables (equal samples inside a pair ->
+    serial path; samples equal to rows of the pairs in flight -> re-read; repeated walk tokens -> register forwarding),
+    None tokens, ragged and empty walks, pair streams that end exactly on / around a 32-pair chunk boundary, and a table
+    large enough for the clean path."""
     from comemb_b200 import _lib
-    c = dict(cases.O2_CASES["o2_d128_small"], N=N, neg=neg, nw=12, L=30, W=4, seed=7000 + N + neg, ragged=True)
+    c = dict(cases.O2_CASES["o2_d128_small"], N=N, neg=neg, nw=12, L=30, W=W, seed=7000 + N + neg, ragged=True)
     if none_every:
         c["none_every"] = none_every
     node, ctx, table, walks = cases.o2_inputs(c)
@@ -99,6 +102,23 @@ def test_o2_ordered_d128_kernel_variants_hazards(K, variant, N, neg, none_every)
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
     O.o2_walks(node, ctx, flat, off, seeds, c["lr"], neg, c["W"], table, 1.0, O.DOT_REFBLAS_QUIRK)
     assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+
+
+@pytest.mark.parametrize("lens", [[2], [16], [17], [18], [32], [33], [34], [49], [17, 0, 17], [9, 9, 2, 33, 1, 16]])
+def test_o2_ordered_d128_team_kernel_chunk_boundaries(K, lens):
+    """The scheduling warp hands pair descriptors over in chunks of 32; with window 1 a walk of L tokens is 2(L-1)
+    pairs, so these streams end one pair before / exactly on / after a chunk boundary (30, 32, 34, 62, 64, 66, 96 pairs),
+    also across walk boundaries.  Bit for bit against the oracle, tokens counted."""
+    c = dict(cases.O2_CASES["o2_d128_small"], N=500, neg=5, nw=len(lens), W=1, seed=7300 + sum(lens), lens=lens)
+    node, ctx, table, walks = cases.o2_inputs(c)
+    flat, off = cases.flatten_walks(walks)
+    seeds = O.seeds_from_numpy(np.random.RandomState(8), len(walks))
+    dn, dc = dev(node), dev(ctx)
+    n = K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), c["lr"], 5, 1, dev(table), mode=K.MODE_ORDERED,
+                   count_tokens=True)
+    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], 5, 1, table, 1.0, O.DOT_REFBLAS_QUIRK)
+    assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+    assert n == sum(lens)
 
 
 @pytest.mark.parametrize("variant", [0, 800])
