@@ -50,9 +50,11 @@ int comemb_abi_version(void);
 /* Hogwild work decomposition: centres_per_unit = 0 -> one warp per walk (the reference's per-thread granularity);
  * > 0 -> one warp per chunk of that many centres (needs max_walk_len; the chunk starts at the right position of the
  * walk's LCG stream).  blocks_per_sm % 100: resident CTAs per SM (0 = occupancy query).  blocks_per_sm / 100 selects an
- * experimental kernel variant: 0 default, 5 = L2 eviction-priority hints on the size-128 o2 kernel, 9 = force the
- * generic kernels where a size-128 specialisation exists (used by the tests to cover both).  Process-global state, not
- * thread-safe: set it before launching, from one thread. */
+ * experimental kernel variant: 0 default, 5 = L2 eviction-priority hints on the size-128 o2 kernel, 7 / 8 = ORDERED
+ * mode at size 128 on a single warp with / without the software pipeline (default: scheduling warp + one worker warp
+ * per target row for o2, pipelined single warp for o1; all give the same bits), 9 = force the generic kernels where
+ * a size-128 specialisation exists (used by the tests to cover both).  Process-global state, not thread-safe: set it
+ * before launching, from one thread. */
 int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm);
 /* HOGWILD concurrency cap: at most `max_warps` walks/edges are processed at the same time (0 = fill the GPU).  The
  * reference's `workers` count plays this role; the learners set max(workers, n_rows/28) so that the expected number
