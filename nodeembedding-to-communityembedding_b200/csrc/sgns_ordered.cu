@@ -9,7 +9,12 @@
 // reinterpretation.  saxpy is one FMA per element.  Every step is an IEEE-754 operation with a single defined
 // rounding, so the device result equals the CPU result exactly.
 //
-// This is a correctness mode: a single warp, no parallelism across pairs (pair p+1 must see every write of pair p).
+// This is a correctness mode: no parallelism across pairs (pair p+1 must see every write of pair p).  Kernels:
+//   o2/o1_ordered_kernel, sg_fused_ordered_kernel, sg_twin_kernel   any size, one warp, rows in global/shared memory
+//   o2/o1_ordered_d128_kernel                                       size 128, one warp, rows in registers
+//   o2/o1_ordered_d128_pipe_kernel                                  + next pair's rows requested before the current one
+//   o2_ordered_d128_team_kernel (default for o2, window <= 15)      scheduling warp + one worker warp per target row
+// They all produce the same bits (tests/test_gpu_parity.py::test_o2_ordered_d128_kernel_variants_hazards).
 #include "comemb_common.cuh"
 
 bool g_force_generic_ordered = false;  // tests: comemb_set_tuning(.., .., 900) routes size 128 to the generic kernels
