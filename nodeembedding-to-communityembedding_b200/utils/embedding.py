@@ -64,9 +64,14 @@ def paths_to_rows(model, paths):
     if isinstance(paths, np.ndarray) and paths.ndim == 2 and paths.dtype.kind in "iu":
         # a rectangular corpus (edge list, fixed-length walks): map every token at once
         a = paths.astype(np.int64, copy=False)
-        pos = np.searchsorted(ids, a.ravel())
-        pos[pos >= ids.size] = 0
-        keep = ids[pos] == a.ravel()
+        if ids.size and int(ids[-1]) - int(ids[0]) + 1 == ids.size:  # dense ids (the usual 1..N): no search needed
+            pos = a.ravel() - int(ids[0])
+            keep = (pos >= 0) & (pos < ids.size)
+            pos = np.where(keep, pos, 0)
+        else:
+            pos = np.searchsorted(ids, a.ravel())
+            pos[pos >= ids.size] = 0
+            keep = ids[pos] == a.ravel()
         if any_ds:  # one random_sample() per in-vocabulary token with probability < 1, in corpus order
             p = probs[pos]
             cand = np.flatnonzero(keep & (p < 1.0))

@@ -185,3 +185,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "sgns_pair_updates_per_sec" and line["value"] > 1e4
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_paths_to_rows_rectangular_fast_paths_equal_the_per_path_loop():
+    """Edge lists / fixed-length walks are mapped in one vectorised pass (dense ids 1..N without a search, sparse ids
+    with searchsorted); both must equal the per-path loop that mirrors prepare_sentences (embedding.py:126-136),
+    including OOV drops and the order of the down-sampling draws."""
+    from comemb_b200.utils.embedding import paths_to_rows
+
+    class FakeModel(object):
+        def __init__(self, ids, probs):
+            self.ids, self.probs = np.asarray(ids, np.int64), probs
+
+        def id_index(self):
+            return self.ids, np.arange(self.ids.size, dtype=np.int64), self.probs
+
+    rs = np.random.RandomState(0)
+    for ids in (np.arange(1, 101), np.array(sorted(rs.choice(500, 100, replace=False)))):
+        a = rs.randint(-3, 520, size=(50, 7))
+        for probs in (np.ones(ids.size), np.where(np.arange(ids.size) % 3 == 0, 1.0, rs.uniform(0.3, 1.0, ids.size))):
+            m = FakeModel(ids, probs)
+            np.random.seed(5)
+            f1, o1 = paths_to_rows(m, a)
+            np.random.seed(5)
+            f2, o2 = paths_to_rows(m, [list(r) for r in a])
+            assert np.array_equal(f1, f2) and np.array_equal(o1, o2)
