@@ -68,5 +68,17 @@ class Community2Vec(object):
         rows_d = torch.from_numpy(rows.view(np.int32)).to(dev)
         with torch.cuda.device(dev):
             inv_t = K.transpose_blocks(model.inv_covariance_mat.contiguous())
-            K.o3_batch(model.node_embedding, rows_d, model.centroid.contiguous(), inv_t, model.pi.contiguous(), beta,
-                       self.lr, iters=iter)
+            pi = model.pi.contiguous()
+            # Rows whose pi has at most one non-zero entry (sklearn's predict_proba is one-hot in fp32 on separated
+            # data) take the top-1 form: same arithmetic, but rows are grouped by community on the device and share
+            # the inv_cov reads.  The others keep the dense form.
+            single_all = (pi != 0).sum(1) <= 1
+            single = single_all[rows_d.long()]
+            mu = model.centroid.contiguous()
+            if bool(single.any()):
+                pi1 = pi if bool(single_all.all()) else pi * single_all[:, None].to(pi.dtype)
+                comm, weight = K.pi_top1(pi1)
+                sel = rows_d if bool(single.all()) else rows_d[single].contiguous()
+                K.o3_batch_top1(model.node_embedding, sel, mu, inv_t, comm, weight, beta, self.lr, iters=iter)
+            if not bool(single.all()):
+                K.o3_batch(model.node_embedding, rows_d[~single].contiguous(), mu, inv_t, pi, beta, self.lr, iters=iter)

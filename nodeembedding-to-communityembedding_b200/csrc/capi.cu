@@ -29,6 +29,7 @@ void hogwild_set_max_warps(int64_t);
 extern bool g_force_generic_ordered;
 extern int g_ordered_variant;
 extern bool g_force_generic_fused;
+extern bool g_force_generic_o3;
 extern int64_t g_fused_n_rows;
 int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
                    const float *, const float *, const float *, int, int, cudaStream_t);
@@ -113,6 +114,7 @@ int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm)
     g_force_generic_ordered = (blocks_per_sm / 100) == 9;
     g_ordered_variant = ((blocks_per_sm / 100) == 7 || (blocks_per_sm / 100) == 8) ? blocks_per_sm / 100 : 0;
     g_force_generic_fused = (blocks_per_sm / 100) == 9;
+    g_force_generic_o3 = (blocks_per_sm / 100) == 9;
     return 0;
 }
 

@@ -14,6 +14,10 @@
 // Not HBM-bound: 2*K_live*d^2 flop per row against L2-resident inv_cov (K*d*d*4 B: 3.3 MB at K=50, d=128).
 #include "comemb_common.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
+bool g_force_generic_o3 = false;  // tests: comemb_set_tuning(.., .., 900) keeps the one-row-per-warp kernel
+
 namespace {
 
 constexpr int O3_WARPS = 8;
@@ -22,7 +26,7 @@ constexpr int O3_MAX_SLICES = 16;  // size <= 512
 __global__ void __launch_bounds__(O3_WARPS * 32)
     o3_batch_kernel(float *node, int64_t n_rows, int size, const uint32_t *rows, int64_t n_sel, const float *mu,
                     const float *inv_cov_t, const float *pi, const int32_t *comm, const float *weight, int K,
-                    float scale, float lr, int iters) {
+                    float scale, float lr, int iters, const uint32_t *skip_unless_key, uint32_t key) {
     extern __shared__ float smem[];
     float *diff = smem + (size_t)(threadIdx.x >> 5) * size;  // this warp's (x - mu_k)
     const int lane = threadIdx.x & 31;
@@ -30,6 +34,7 @@ __global__ void __launch_bounds__(O3_WARPS * 32)
     const int64_t n_warps = (int64_t)gridDim.x * O3_WARPS;
     const int n_slices = (size + 31) / 32;
     for (int64_t s = warp0; s < n_sel; s += n_warps) {
+        if (skip_unless_key && skip_unless_key[s] != key) continue;  // that row belongs to o3_top1_d128_kernel
         const int64_t r = rows ? (int64_t)rows[s] : s;
         float *x = node + r * size;
         // dense pi row, or the top-1 form (one community + weight per row; comm < 0: no community)
@@ -71,6 +76,123 @@ __global__ void __launch_bounds__(O3_WARPS * 32)
                 }
             }
             __syncwarp();
+        }
+    }
+}
+
+// ---- top-1 form, size == 128: rows grouped by community, 8 rows per warp share every inv_cov element -----------------------
+// The kernel above streams all of inv_cov_k (64 KB) from L2 for every single row: 5 TB/s of L2 reads at 8e7 rows/s.
+// Here the selected rows are first sorted by community (cub radix sort of (community, row) pairs; rows whose weight is
+// not exactly 1 or that have no community get key K and stay with the kernel above), each warp takes a CONTIGUOUS range
+// of 8-row tiles (so consecutive tiles reuse the same inv_cov block out of L1), keeps the 8 rows in registers and applies
+// every loaded inv_cov element to all 8.  Same arithmetic as above, bit for bit: with p == 1 the product (float)(p*S)
+// is S, and fma(S, diff, t) on doubles converted from floats equals dadd(t, dmul(S, diff)) because the 48-bit product
+// is exact.
+constexpr int O3F_T = 8, O3F_WARPS = 4;
+
+__global__ void o3_keys_kernel(const uint32_t *rows, int64_t n_sel, const int32_t *comm, const float *weight, int K,
+                               uint32_t *keys, uint32_t *vals) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_sel; s += stride) {
+        const uint32_t r = rows ? rows[s] : (uint32_t)s;
+        const int c = comm[r];
+        keys[s] = (c >= 0 && c < K && weight[r] == 1.0f) ? (uint32_t)c : (uint32_t)K;
+        vals[s] = r;
+    }
+}
+
+__global__ void __launch_bounds__(O3F_WARPS * 32)
+    o3_top1_d128_kernel(float *node, const uint32_t *srows, const uint32_t *skeys, int64_t n_sel, const float *mu,
+                        const float *inv_cov_t, int K, float scale, float lr, int iters, int64_t tiles_per_warp) {
+    constexpr int D = 128;
+    __shared__ double diffd[O3F_WARPS][O3F_T][D];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int64_t wg = (int64_t)blockIdx.x * O3F_WARPS + wl;
+    const int64_t n_tiles = (n_sel + O3F_T - 1) / O3F_T;
+    const int64_t t1 = min(n_tiles, (wg + 1) * tiles_per_warp);
+    for (int64_t tile = wg * tiles_per_warp; tile < t1; tile++) {
+        const int64_t base = tile * O3F_T;
+        uint32_t my_r = 0, my_k = (uint32_t)K;
+        if (lane < O3F_T && base + lane < n_sel) {
+            my_r = srows[base + lane];
+            my_k = skeys[base + lane];
+        }
+        unsigned todo = __ballot_sync(FULL, my_k < (uint32_t)K);  // bit n: row n of the tile is ours and not done yet
+        while (todo) {  // one pass per community present in the tile (two at a boundary)
+            const int n0 = __ffs(todo) - 1;
+            const uint32_t c = __shfl_sync(FULL, my_k, n0);
+            const unsigned run = __ballot_sync(FULL, my_k == c) & todo;
+            todo &= ~run;
+            const float *St = inv_cov_t + (int64_t)c * D * D;
+            float mu_a[4], x[O3F_T][4];
+            int64_t roff[O3F_T];
+#pragma unroll
+            for (int m = 0; m < 4; m++) mu_a[m] = mu[(int64_t)c * D + lane + 32 * m];
+#pragma unroll
+            for (int n = 0; n < O3F_T; n++) {
+                roff[n] = (int64_t)__shfl_sync(FULL, my_r, n) * D;
+#pragma unroll
+                for (int m = 0; m < 4; m++) x[n][m] = ((run >> n) & 1u) ? node[roff[n] + lane + 32 * m] : 0.f;
+            }
+            for (int it = 0; it < iters; it++) {
+                __syncwarp();
+#pragma unroll
+                for (int n = 0; n < O3F_T; n++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++) diffd[wl][n][lane + 32 * m] = (double)(x[n][m] - mu_a[m]);  // :68
+                __syncwarp();
+                double acc[O3F_T][4];
+#pragma unroll
+                for (int n = 0; n < O3F_T; n++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++) acc[n][m] = 0.0;
+                // :69-71, b in index order.  inv_cov elements are requested one chunk of 4 b's ahead (two register sets
+                // that swap by name, so that nothing touches a register whose load is still in flight).
+                float sa[4][4], sb[4][4];
+                auto request = [&](float (&sf)[4][4], int b0) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int m = 0; m < 4; m++) sf[q][m] = __ldg(St + (b0 + q) * D + lane + 32 * m);
+                };
+                auto apply = [&](const float (&sf)[4][4], int b0) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        double sd[4];
+#pragma unroll
+                        for (int m = 0; m < 4; m++) sd[m] = (double)sf[q][m];
+#pragma unroll
+                        for (int n = 0; n < O3F_T; n++) {
+                            const double d = diffd[wl][n][b0 + q];
+#pragma unroll
+                            for (int m = 0; m < 4; m++) acc[n][m] = __fma_rn(sd[m], d, acc[n][m]);
+                        }
+                    }
+                };
+                request(sa, 0);
+#pragma unroll 1
+                for (int b0 = 0; b0 < D; b0 += 8) {
+                    request(sb, b0 + 4);
+                    apply(sa, b0);
+                    if (b0 + 8 < D) request(sa, b0 + 8);
+                    apply(sb, b0 + 4);
+                }
+#pragma unroll
+                for (int n = 0; n < O3F_T; n++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const float grad = 0.f + __double2float_rn(acc[n][m]);
+                        float g = __fmul_rn(grad, scale);            // :76
+                        g = fminf(fmaxf(g, -5.f), 5.f);              // :77 clip
+                        x[n][m] = x[n][m] - __fmul_rn(g, lr);
+                    }
+            }
+#pragma unroll
+            for (int n = 0; n < O3F_T; n++)
+                if ((run >> n) & 1u) {
+#pragma unroll
+                    for (int m = 0; m < 4; m++) node[roff[n] + lane + 32 * m] = x[n][m];
+                }
         }
     }
 }
@@ -149,8 +271,53 @@ int launch_o3_batch(float *node, int64_t n_rows, int size, const uint32_t *rows,
     int64_t want = (n_sel + O3_WARPS - 1) / O3_WARPS;
     int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     size_t smem = (size_t)O3_WARPS * size * sizeof(float);
+    if (!pi && size == 128 && !g_force_generic_o3 && n_sel >= 4 * O3F_T && n_sel < (1LL << 31) && K < (1 << 30)) {
+        // top-1 form at the headline size: group the rows by community, 8 rows per warp (o3_top1_d128_kernel); rows
+        // without a community or with a weight != 1 keep the one-row-per-warp kernel.
+        uint32_t *buf = nullptr;
+        void *tmp = nullptr;
+        size_t tmp_bytes = 0;
+        int bits = 1;
+        {   // keep the stream-ordered pool's memory across calls (default: returned to the driver at every sync)
+            static bool pool_ready[64] = {};
+            if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                    uint64_t keep = 1ull << 30, cur = 0;
+                    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+                    if (cur < keep) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                }
+                pool_ready[dev] = true;
+            }
+        }
+        while ((1LL << bits) <= K) bits++;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                 (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_sel, 0, bits, st));
+        CUDA_TRY(cudaMallocAsync(&buf, 4 * (size_t)n_sel * sizeof(uint32_t), st));
+        if (cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st) != cudaSuccess) {
+            cudaFreeAsync(buf, st);
+            return (int)cudaErrorMemoryAllocation;
+        }
+        uint32_t *k_in = buf, *v_in = buf + n_sel, *k_out = buf + 2 * n_sel, *v_out = buf + 3 * n_sel;
+        o3_keys_kernel<<<sms * 4, 256, 0, st>>>(rows, n_sel, comm, weight, K, k_in, v_in);
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n_sel, 0, bits, st);
+        if (e == cudaSuccess) {
+            const int64_t n_tiles = (n_sel + O3F_T - 1) / O3F_T;
+            const int64_t max_warps = (int64_t)sms * 2 * O3F_WARPS;  // 2 CTAs of 4 warps per SM (191 registers)
+            const int64_t tiles_per_warp = (n_tiles + max_warps - 1) / max_warps;
+            const int64_t warps = (n_tiles + tiles_per_warp - 1) / tiles_per_warp;
+            o3_top1_d128_kernel<<<(int)((warps + O3F_WARPS - 1) / O3F_WARPS), O3F_WARPS * 32, 0, st>>>(
+                node, v_out, k_out, n_sel, mu, inv_cov_t, K, scale, lr, iters, tiles_per_warp);
+            o3_batch_kernel<<<grid, O3_WARPS * 32, smem, st>>>(node, n_rows, size, v_out, n_sel, mu, inv_cov_t, nullptr, comm,
+                                                               weight, K, scale, lr, iters, k_out, (uint32_t)K);
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(tmp, st);
+        cudaFreeAsync(buf, st);
+        return (int)e;
+    }
     o3_batch_kernel<<<grid, O3_WARPS * 32, smem, st>>>(node, n_rows, size, rows, n_sel, mu, inv_cov_t, pi, comm, weight, K, scale, lr,
-                                                       iters);
+                                                       iters, nullptr, 0u);
     return (int)cudaGetLastError();
 }
 

@@ -1070,3 +1070,42 @@ def test_top1_forms_of_pi_equal_the_dense_forms(K):
     assert torch.equal(n1, n2) and torch.equal(c1, c2)
     with pytest.raises(K.ComembError):
         K.pi_top1(dev(np.full((4, 3), 1 / 3, np.float32)))
+
+
+@pytest.mark.parametrize("iters", [1, 3])
+def test_o3_top1_grouped_kernel_equals_one_row_per_warp_kernel(K, iters):
+    """Top-1 form at size 128: rows are sorted by community on the device and processed 8 per warp
+    (o3_top1_d128_kernel); rows with weight != 1 or without a community stay with the generic kernel.  Both against the
+    generic kernel alone (tuning variant 9) and the oracle: bit for bit."""
+    import torch
+    from comemb_b200 import _lib
+    rs = np.random.RandomState(77)
+    N, d, Kc = 3001, 128, 7
+    node = (rs.uniform(-1, 1, (N, d)) * 0.3).astype(np.float32)
+    mu = rs.uniform(-0.5, 0.5, (Kc, d)).astype(np.float32)
+    inv = (rs.normal(size=(Kc, d, d)) * 0.05 + np.eye(d)).astype(np.float32)
+    comm = rs.randint(0, Kc, size=N).astype(np.int32)
+    weight = np.ones(N, np.float32)
+    weight[::11] = rs.uniform(0.2, 0.99, size=weight[::11].size).astype(np.float32)  # not one-hot: generic kernel
+    comm[::17] = -1                                                                   # no community: untouched
+    weight[::17] = 0.0
+    rows = rs.permutation(N)[: N - 200].astype(np.uint32)  # a selection, in arbitrary order
+    inv_t = K.transpose_blocks(dev(inv))
+    out = []
+    for variant in (0, 900):
+        _lib.check(_lib.load().comemb_set_tuning(0, 0, variant))
+        try:
+            dn = dev(node)
+            K.o3_batch_top1(dn, dev(rows), dev(mu), inv_t, dev(comm), dev(weight), 0.1, 0.05, iters=iters)
+            out.append(host(dn))
+        finally:
+            _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
+    assert np.array_equal(out[0], out[1])
+    pi = np.zeros((N, Kc), np.float32)
+    ok = comm >= 0
+    pi[np.flatnonzero(ok), comm[ok]] = weight[ok]
+    ref = node.copy()
+    O.o3_batch(ref, rows, mu, inv, pi, 0.1, 0.05, iters)
+    assert np.array_equal(out[0], ref)
+    untouched = np.setdiff1d(np.arange(N), rows)
+    assert np.array_equal(out[0][untouched], node[untouched])
