@@ -117,7 +117,10 @@ int comemb_o3_batch(float *d_node, int64_t n_rows, int size, const uint32_t *d_r
                     const float *d_mu, const float *d_inv_cov_t, const float *d_pi, int K, double beta, float lr,
                     int iters, void *stream);
 /* The same update with pi in TOP-1 form (what fp32 predict_proba gives on separated data, and the only form that fits
- * at 50M nodes x 1000 communities): d_comm[r] = the row's community or -1, d_weight[r] = its responsibility. */
+ * at 50M nodes x 1000 communities): d_comm[r] = the row's community or -1, d_weight[r] = its responsibility.
+ * At size 128 the selected rows are sorted by community on the device (16 bytes of stream-ordered scratch per row,
+ * cudaMallocAsync on `stream`) and rows with weight exactly 1 are processed 8 per warp sharing the inv_cov reads; the
+ * result is the same bit for bit.  A row must not appear twice in d_rows. */
 int comemb_o3_batch_top1(float *d_node, int64_t n_rows, int size, const uint32_t *d_rows, int64_t n_sel,
                          const float *d_mu, const float *d_inv_cov_t, const int32_t *d_comm, const float *d_weight, int K,
                          double beta, float lr, int iters, void *stream);
