@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(WARPS * 32) sg_fused_hogwild_kernel(const SgPa
 // Differences to the sequential reference, both inside Hogwild tolerance: the o3 term of a window is computed from
 // the x_j at the start of the centre (identical unless one node occupies two window positions), and inv_cov / diff
 // enter the tensor cores as TF32 (relative error ~1e-3 of a term that is clipped to 0.1*lr).
-constexpr int FW = 5;         // warps per block: 3 blocks/SM = 15 warps (13.5 KB staging per warp, 128 registers)
+constexpr int FW = 6;         // warps per block: 2 blocks/SM = 12 warps (13.5 KB staging per warp, <= 168 registers)
 constexpr int VMAX = 24;      // window positions held per centre
 constexpr int DSTRIDE = 132;  // floats per staging row: 128 + 4 pad -> B-fragment loads hit 32 distinct banks
 
@@ -275,7 +275,7 @@ struct SgFastParams {
 };
 
 template <bool ATOMIC, int NEG>
-__global__ void __launch_bounds__(FW * 32, 3) sg_fused_d128_kernel(const SgFastParams P) {
+__global__ void __launch_bounds__(FW * 32, 2) sg_fused_d128_kernel(const SgFastParams P) {
     constexpr int D = 128;
     constexpr LcgJump<NEG> J{};
     __shared__ float lut[EXP_TABLE_SIZE];
@@ -367,22 +367,34 @@ __global__ void __launch_bounds__(FW * 32, 3) sg_fused_d128_kernel(const SgFastP
                         for (int mt = 0; mt < 8; mt++)
 #pragma unroll
                             for (int q = 0; q < 4; q++) acc0[mt][q] = acc1[mt][q] = 0.f;
-#pragma unroll 2
-                        for (int kt = 0; kt < 16; kt++) {
+                        // operand A = inv_cov_c^T (A[a][b] = S[b][a], the reference's column-major read) comes from the
+                        // FRAGMENT-MAJOR, TF32-rounded copy built by tile_inv_cov_kernel: for every (kt, mt) the 32 lanes'
+                        // operand quads are 512 consecutive bytes -> one fully coalesced 128-bit load per MMA, landing
+                        // directly in its operand register quad.  The 8 quads of slice kt+1 are requested before the MMAs
+                        // of slice kt run (two register sets that swap by name).
+                        const float4 *af = reinterpret_cast<const float4 *>(Sc) + lane;
+                        float4 aA[8], aB[8];
+                        auto request = [&](float4 (&a)[8], int kt) {
+#pragma unroll
+                            for (int mt = 0; mt < 8; mt++) a[mt] = __ldg(af + (size_t)kt * 256 + mt * 32);
+                        };
+                        auto sweep = [&](const float4 (&a)[8], int kt) {
                             const int b0 = 8 * kt;
                             const uint32_t bb0 = to_tf32(d0[b0 + t]), bb1 = to_tf32(d0[b0 + t + 4]);
                             const uint32_t cc0 = to_tf32(d1[b0 + t]), cc1 = to_tf32(d1[b0 + t + 4]);
-                            // operand A = inv_cov_c^T (A[a][b] = S[b][a], the reference's column-major read) comes from
-                            // the FRAGMENT-MAJOR, TF32-rounded copy built by tile_inv_cov_kernel: for every (kt, mt) the
-                            // 32 lanes' operand quads are 512 consecutive bytes -> one fully coalesced 128-bit load
-                            // per MMA, landing directly in its operand register quad.
-                            const float4 *af = reinterpret_cast<const float4 *>(Sc) + (size_t)kt * 256 + lane;
 #pragma unroll
                             for (int mt = 0; mt < 8; mt++) {
-                                const float4 a4 = __ldg(af + mt * 32);
-                                mma_tf32(acc0[mt], a4, bb0, bb1);
-                                if (two) mma_tf32(acc1[mt], a4, cc0, cc1);
+                                mma_tf32(acc0[mt], a[mt], bb0, bb1);
+                                if (two) mma_tf32(acc1[mt], a[mt], cc0, cc1);
                             }
+                        };
+                        request(aA, 0);
+#pragma unroll 1
+                        for (int kt = 0; kt < 16; kt += 2) {
+                            request(aB, kt + 1);
+                            sweep(aA, kt);
+                            if (kt + 2 < 16) request(aA, kt + 2);
+                            sweep(aB, kt + 1);
                         }
                         __syncwarp();  // every lane is done reading these members' diff rows
                         // C fragment of tile mt: c0:(a=16g+2mt, col 2t) c1:(same a, col 2t+1) c2:(a+1, col 2t) c3:(a+1, col 2t+1)
