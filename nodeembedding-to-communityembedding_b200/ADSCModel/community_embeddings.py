@@ -64,7 +64,7 @@ class Community2Vec(object):
     def train(self, nodes, model, beta, chunksize=150, iter=1):
         import torch
         dev = model.node_embedding.device
-        rows = np.fromiter((model.vocab[x].index for x in nodes), dtype=np.uint32)
+        rows = _rows_of(model, nodes)
         rows_d = torch.from_numpy(rows.view(np.int32)).to(dev)
         with torch.cuda.device(dev):
             inv_t = K.transpose_blocks(model.inv_covariance_mat.contiguous())
@@ -82,3 +82,21 @@ class Community2Vec(object):
                 K.o3_batch_top1(model.node_embedding, sel, mu, inv_t, comm, weight, beta, self.lr, iters=iter)
             if not bool(single.all()):
                 K.o3_batch(model.node_embedding, rows_d[~single].contiguous(), mu, inv_t, pi, beta, self.lr, iters=iter)
+
+
+def _rows_of(model, nodes):
+    """[model.vocab[x].index for x in nodes] (community_embeddings.py:63) without a Python loop for integer ids; an id
+    that is not in the vocabulary raises KeyError like the reference's dict lookup."""
+    try:
+        a = np.asarray(nodes if isinstance(nodes, np.ndarray) else list(nodes))
+    except Exception:
+        a = None
+    if a is None or a.ndim != 1 or a.dtype.kind not in "iu" or a.size == 0:
+        return np.fromiter((model.vocab[x].index for x in nodes), dtype=np.uint32)
+    ids, rows, _ = model.id_index()
+    pos = np.searchsorted(ids, a)
+    pos[pos >= ids.size] = 0
+    bad = ids[pos] != a
+    if bad.any():
+        raise KeyError(a[bad][0].item())
+    return rows[pos].astype(np.uint32)
