@@ -91,7 +91,7 @@ def _rows_of(model, nodes):
         a = np.asarray(nodes if isinstance(nodes, np.ndarray) else list(nodes))
     except Exception:
         a = None
-    if a is None or a.ndim != 1 or a.dtype.kind not in "iu" or a.size == 0:
+    if a is None or a.ndim != 1 or a.dtype.kind not in "iu" or a.size == 0 or not hasattr(model, "id_index"):
         return np.fromiter((model.vocab[x].index for x in nodes), dtype=np.uint32)
     ids, rows, _ = model.id_index()
     pos = np.searchsorted(ids, a)

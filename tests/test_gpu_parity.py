@@ -106,7 +106,8 @@ def test_o2_ordered_d128_kernel_variants_hazards(K, variant, N, neg, none_every,
     assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
 
 
-@pytest.mark.parametrize("lens", [[2], [16], [17], [18], [32], [33], [34], [49], [17, 0, 17], [9, 9, 2, 33, 1, 16]])
+@pytest.mark.parametrize("lens", [[0, 0], [1], [1, 0, 1], [2], [16], [17], [18], [32], [33], [34], [49], [17, 0, 17],
+                                  [9, 9, 2, 33, 1, 16]])
 def test_o2_ordered_d128_team_kernel_chunk_boundaries(K, lens):
     """The scheduling warp hands pair descriptors over in chunks of 32; with window 1 a walk of L tokens is 2(L-1)
     pairs, so these streams end one pair before / exactly on / after a chunk boundary (30, 32, 34, 62, 64, 66, 96 pairs),
