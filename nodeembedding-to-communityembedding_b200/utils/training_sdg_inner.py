@@ -168,6 +168,8 @@ def o2_batch(node, ctx, walks, walk_off, seeds, lr, negative, window, table, alp
     torch = _torch()
     _lib.ensure_init()
     n_walks = int(walk_off.numel()) - 1
+    if n_walks <= 0 or walks.numel() == 0:  # an empty corpus (or only empty walks): nothing to update, 0 tokens
+        return 0 if count_tokens else None
     if seeds is None:
         flags |= F_SEED_HASH
     if alias is not None:
