@@ -589,12 +589,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tuning", type=int, nargs=3, default=None, metavar=("CENTRES", "MAXLEN", "BLOCKS"),
                     help="comemb_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm) for experiments")
+    ap.add_argument("--lr", type=float, default=None,
+                    help="experiment knob (default: the workload's 0.025); 0 skips every negative-row update")
     args = ap.parse_args()
     global PARTITION
     PARTITION = args.partition
     if args.workload == "youtube":
         CFG.clear()
         CFG.update(CFG_YOUTUBE)
+    if args.lr is not None:
+        CFG["lr"] = args.lr
     if args.impl == "reference":
         run_reference(args)
     elif args.kernel != "o2":
