@@ -814,9 +814,13 @@ int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, 
     const bool vec = (size % 4) == 0;
     if (size == 128 && g_tuning.variant != 9) {  // the headline shape (variant 9 forces the generic kernel: tests)
         switch (negative) {
+            case 1: return launch_o2_d128<1>(P, atomic, st);
+            case 2: return launch_o2_d128<2>(P, atomic, st);
             case 3: return launch_o2_d128<3>(P, atomic, st);
             case 4: return launch_o2_d128<4>(P, atomic, st);
             case 5: return launch_o2_d128<5>(P, atomic, st);
+            case 6: return launch_o2_d128<6>(P, atomic, st);
+            case 7: return launch_o2_d128<7>(P, atomic, st);
             default: break;
         }
     }

@@ -359,12 +359,19 @@ def test_o2_hogwild_generic_kernel_at_d128(K, name):
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
 
 
-@pytest.mark.parametrize("neg,d", [(1, 128), (2, 128), (7, 128), (12, 64), (3, 128), (4, 128)])
-def test_o2_hogwild_other_negative_counts(K, neg, d):
-    """negative = 3..5 at size 128 take the specialised kernel (compile-time NEG); everything else the generic kernel,
-    which gathers negatives in batches of 5 (7 and 12: several batches).  Single warp vs the oracle, bit for bit."""
+@pytest.mark.parametrize("variant", [0, 900])
+@pytest.mark.parametrize("neg,d", [(1, 128), (2, 128), (6, 128), (7, 128), (12, 64), (8, 128), (3, 128), (4, 128)])
+def test_o2_hogwild_other_negative_counts(K, neg, d, variant):
+    """negative = 1..7 at size 128 take the specialised kernel (compile-time NEG); everything else -- and variant 9 --
+    the generic kernel, which gathers negatives in batches of 5 (7, 8 and 12: several batches).  Single warp vs the
+    oracle, bit for bit."""
+    from comemb_b200 import _lib
     c = dict(cases.O2_CASES["o2_d128_small"], neg=neg, d=d, seed=900 + neg)
-    _o2_single_warp(K, c, False)
+    _lib.check(_lib.load().comemb_set_tuning(0, 0, variant))
+    try:
+        _o2_single_warp(K, c, False)
+    finally:
+        _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
 
 
 def _o2_single_warp(K, name, atomic):
