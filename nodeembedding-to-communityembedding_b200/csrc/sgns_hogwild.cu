@@ -853,7 +853,7 @@ int launch_o1_hogwild(float *node, int size, const uint32_t *edges, int64_t n_ed
         }                                                                             \
         return (int)cudaGetLastError();
         switch (negative) {
-            COMEMB_O1(3) COMEMB_O1(4) COMEMB_O1(5)
+            COMEMB_O1(1) COMEMB_O1(2) COMEMB_O1(3) COMEMB_O1(4) COMEMB_O1(5) COMEMB_O1(6) COMEMB_O1(7)
             default: break;
         }
 #undef COMEMB_O1

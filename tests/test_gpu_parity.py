@@ -432,12 +432,12 @@ def test_o2_hogwild_chunked_units_keep_the_reference_lcg_stream(K):
 
 @pytest.mark.parametrize("variant", [0, 900])
 def test_o1_hogwild_d128_specialised_and_generic_kernels(K, variant):
-    """size 128 with negative in 3..5 takes the specialised o1 kernel; variant 9 forces the generic one.  Edge lists
+    """size 128 with negative in 1..7 takes the specialised o1 kernel; variant 9 forces the generic one.  Edge lists
     with self loops and with samples that hit the edge's own endpoints (tiny table), one edge per launch: bit-exact."""
     from comemb_b200 import _lib
     _lib.check(_lib.load().comemb_set_tuning(0, 0, variant))
     try:
-        for neg, N in ((5, 100), (4, 12), (3, 6)):
+        for neg, N in ((5, 100), (4, 12), (3, 6), (1, 30), (2, 8), (6, 40), (7, 10)):
             c = dict(cases.O1_CASES["o1_d128"], neg=neg, N=N, E=80, seed=950 + neg, selfloop_every=7)
             node, table, edges = cases.o1_inputs(c)
             seeds = O.seeds_from_numpy(np.random.RandomState(4), len(edges))
