@@ -20,7 +20,7 @@ import numpy as np
 
 class DeviceGaussianMixture(object):
     def __init__(self, n_components=1, reg_covar=1e-6, tol=1e-3, max_iter=100, n_init=1, random_state=None,
-                 dtype=None, kmeans_iter=20, workspace_bytes=6 << 30, tf32=False):
+                 dtype=None, kmeans_iter=20, workspace_bytes=6 << 30, tf32=False, sparse_m_step=True):
         self.n_components = int(n_components)
         self.reg_covar = float(reg_covar)
         self.tol = float(tol)
@@ -30,30 +30,57 @@ class DeviceGaussianMixture(object):
         self.dtype = dtype
         self.kmeans_iter = kmeans_iter
         self.workspace_bytes = int(workspace_bytes)  # bound on the temporaries of the batched E / M steps
+        self.sparse_m_step = bool(sparse_m_step)
         self.tf32 = bool(tf32)  # let cuBLAS use TF32 tensor cores for the fp32 GEMMs (about 1.7x per EM iteration;
         #                         the sklearn comparison of tests/test_gmm_device.py holds for tf32=False)
         self.converged_ = False
 
     # ---- sklearn: _estimate_gaussian_parameters + _estimate_gaussian_covariances_full ----------------------------------
     def _estimate_parameters(self, X, resp):
-        """covariances[k] = (resp[:, k] * diff_k.T) @ diff_k / nk[k] + reg_covar * I with diff_k = X - means[k], for
-        as many components at a time as fit the workspace: one batched GEMM [kc, d, N] x [kc, N, d] instead of kc
-        launches of a 128 x 128-output GEMM."""
+        """covariances[k] = (resp[:, k] * diff_k.T) @ diff_k / nk[k] + reg_covar * I with diff_k = X - means[k].
+        Dense form: as many components at a time as fit the workspace, one batched GEMM [kc, d, N] x [kc, N, d] instead
+        of kc launches of a 128 x 128-output GEMM.  Sparse form: responsibilities that are exactly 0 (exp() underflows
+        for every far component once the clusters separate) contribute exactly 0, so when few are non-zero only those
+        (point, component) pairs are gathered -- padded per component -- into one batched GEMM [K, d, M] x [K, M, d]."""
         import torch
         nk = resp.sum(0) + 10 * torch.finfo(resp.dtype).eps
         means = (resp.T @ X) / nk[:, None]
         K, d = means.shape
         n = X.shape[0]
-        covs = torch.empty((K, d, d), dtype=X.dtype, device=X.device)
-        kc = max(1, min(K, int(self.workspace_bytes // (2 * n * d * X.element_size()))))
-        respT = resp.T.contiguous()
-        for k0 in range(0, K, kc):
-            diff = X[None, :, :] - means[k0:k0 + kc, None, :]
-            wd = diff * respT[k0:k0 + kc, :, None]
-            covs[k0:k0 + kc] = torch.bmm(wd.transpose(1, 2), diff) / nk[k0:k0 + kc, None, None]
-            del diff, wd
+        covs = None
+        if self.sparse_m_step and n * K >= (1 << 16):
+            covs = self._covariances_sparse(X, resp, nk, means)
+        if covs is None:
+            covs = torch.empty((K, d, d), dtype=X.dtype, device=X.device)
+            kc = max(1, min(K, int(self.workspace_bytes // (2 * n * d * X.element_size()))))
+            respT = resp.T.contiguous()
+            for k0 in range(0, K, kc):
+                diff = X[None, :, :] - means[k0:k0 + kc, None, :]
+                wd = diff * respT[k0:k0 + kc, :, None]
+                covs[k0:k0 + kc] = torch.bmm(wd.transpose(1, 2), diff) / nk[k0:k0 + kc, None, None]
+                del diff, wd
         covs.diagonal(dim1=1, dim2=2).add_(self.reg_covar)
         return nk, means, covs
+
+    def _covariances_sparse(self, X, resp, nk, means):
+        """None if the responsibilities are not sparse enough to pay off (more than a quarter non-zero, or one component
+        holding more than half of the points)."""
+        import torch
+        n, K = resp.shape
+        nz = resp != 0
+        per_k = nz.sum(0)
+        m = int(per_k.max())  # one host sync per M-step
+        if m == 0 or m * K > n * K // 4 or m > n // 2:
+            return None
+        kk, nn = nz.T.nonzero(as_tuple=True)  # sorted by component, then point
+        start = torch.cumsum(per_k, 0) - per_k
+        slot = torch.arange(kk.numel(), device=X.device) - start[kk]
+        rows = torch.zeros((K, m), dtype=torch.int64, device=X.device)
+        w = torch.zeros((K, m), dtype=X.dtype, device=X.device)
+        rows[kk, slot] = nn
+        w[kk, slot] = resp[nn, kk]
+        diff = X[rows] - means[:, None, :]  # [K, m, d]; padding slots have weight 0
+        return torch.bmm((diff * w[:, :, None]).transpose(1, 2), diff) / nk[:, None, None]
 
     # ---- sklearn: _compute_precision_cholesky ('full') ------------------------------------------------------------------
     @staticmethod
@@ -76,13 +103,12 @@ class DeviceGaussianMixture(object):
         P = self.precisions_cholesky_
         log_det = torch.log(torch.diagonal(P, dim1=-2, dim2=-1)).sum(1)
         Pcat = P.permute(1, 0, 2).reshape(d, K * d)
-        b = torch.bmm(self.means_[:, None, :], P).reshape(K * d)
+        b_neg = -torch.bmm(self.means_[:, None, :], P).reshape(1, K * d)
         log_prob = torch.empty((n, K), dtype=X.dtype, device=X.device)
         rows = max(1, int(self.workspace_bytes // (K * d * X.element_size())))
         for n0 in range(0, n, rows):
-            y = X[n0:n0 + rows] @ Pcat
-            y.sub_(b).square_()
-            log_prob[n0:n0 + rows] = y.view(-1, K, d).sum(2)
+            y = torch.addmm(b_neg, X[n0:n0 + rows], Pcat)  # X @ Pcat - b, the bias added in the GEMM epilogue
+            log_prob[n0:n0 + rows] = torch.linalg.vector_norm(y.view(-1, K, d), dim=2).square_()  # one pass over y
             del y
         weighted = -0.5 * (d * math.log(2 * math.pi) + log_prob) + log_det + torch.log(self.weights_)
         norm = torch.logsumexp(weighted, dim=1)

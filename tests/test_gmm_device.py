@@ -51,6 +51,51 @@ def test_device_gmm_em_steps_match_sklearn_cpu_float32():
     _compare("cpu", np.float32, 2e-3)
 
 
+def _sparse_m_step(device):
+    """Well separated blobs: most responsibilities underflow to exactly 0, the M-step then gathers only the non-zero
+    (point, component) pairs.  Must equal the dense batched form and sklearn's own M-step."""
+    import torch
+    from sklearn.mixture import GaussianMixture
+    from comemb_b200.ADSCModel.gmm_device import DeviceGaussianMixture
+    rs = np.random.RandomState(5)
+    n, d, k = 6000, 12, 16
+    centres = rs.normal(size=(k, d)) * 40
+    lab = rs.randint(0, k, n)
+    x = centres[lab] + rs.normal(size=(n, d))
+    sk = GaussianMixture(n_components=k, covariance_type="full", reg_covar=1e-6, tol=0.0, max_iter=3)
+    one_hot = np.eye(k)[lab]
+    sk._initialize(x, one_hot)
+    for _ in range(2):
+        _, log_resp = sk._e_step(x)
+        sk._m_step(x, log_resp)
+    resp = np.exp(log_resp)
+    assert (resp == 0).mean() > 0.9
+    X, R = torch.as_tensor(x, device=device), torch.as_tensor(resp, device=device)
+    out = {}
+    for sparse in (True, False):
+        gm = DeviceGaussianMixture(n_components=k, reg_covar=1e-6, sparse_m_step=sparse)
+        if sparse:
+            nk = R.sum(0) + 10 * torch.finfo(R.dtype).eps
+            assert gm._covariances_sparse(X, R, nk, (R.T @ X) / nk[:, None]) is not None  # the sparse path is taken
+        out[sparse] = [t.cpu().numpy() for t in gm._estimate_parameters(X, R)]
+    for a, b in zip(out[True], out[False]):
+        assert np.abs(a - b).max() <= 1e-10 * max(1.0, np.abs(b).max())
+    assert np.abs(out[True][2] - sk.covariances_).max() <= 1e-9 * np.abs(sk.covariances_).max()
+    # dense responsibilities: the sparse form declines
+    gm = DeviceGaussianMixture(n_components=k)
+    dense = torch.full_like(R, 1.0 / k)
+    assert gm._covariances_sparse(X, dense, dense.sum(0), (dense.T @ X) / dense.sum(0)[:, None]) is None
+
+
+def test_device_gmm_sparse_m_step_cpu():
+    _sparse_m_step("cpu")
+
+
+@pytest.mark.gpu
+def test_device_gmm_sparse_m_step_gpu():
+    _sparse_m_step("cuda")
+
+
 def test_device_gmm_full_fit_recovers_blobs_cpu():
     import torch
     from sklearn.metrics import normalized_mutual_info_score as nmi
