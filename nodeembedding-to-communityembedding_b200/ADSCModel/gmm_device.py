@@ -134,13 +134,24 @@ class DeviceGaussianMixture(object):
             d2 = torch.minimum(d2, ((X - centres[k]) ** 2).sum(1))
         xx = (X * X).sum(1, keepdim=True)
         one = None
+        S = 64  # the [K, N] x [N, d] centre sums are split over the N dimension into S independent GEMMs (one
+        #         [K, d]-output GEMM with a 100K-long reduction runs on a handful of SMs)
+        n_main = (n // S) * S
         for it in range(self.kmeans_iter):
-            dist = xx - 2 * (X @ centres.T) + (centres * centres).sum(1)[None, :]
+            dist = torch.addmm(xx, X, centres.T, alpha=-2.0)  # ||x||^2 - 2 x.c  (+ ||c||^2 below)
+            dist.add_((centres * centres).sum(1)[None, :])
             lab = dist.argmin(1)
             one = torch.zeros((n, K), dtype=X.dtype, device=X.device)
             one[torch.arange(n, device=X.device), lab] = 1
             cnt = one.sum(0)
-            new = (one.T @ X) / cnt.clamp(min=1)[:, None]  # a GEMM: scatter-adds into K rows would serialise
+            if n_main >= S * 64:
+                sums = torch.bmm(one[:n_main].view(S, n_main // S, K).transpose(1, 2),
+                                 X[:n_main].view(S, n_main // S, -1)).sum(0)
+                if n_main < n:
+                    sums = sums + one[n_main:].T @ X[n_main:]
+            else:
+                sums = one.T @ X
+            new = sums / cnt.clamp(min=1)[:, None]
             new = torch.where((cnt == 0)[:, None], centres, new)
             done = (it % 5 == 4) and bool(torch.allclose(new, centres))
             centres = new
