@@ -156,4 +156,14 @@ __device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t pol
     return v;
 }
 
+// ---- cp.async (LDGSTS): global -> shared without a register or a load scoreboard ------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 int comemb_check_init();  // COMEMB_E_NOINIT unless comemb_init() ran on the current device

@@ -514,15 +514,6 @@ __global__ void __launch_bounds__(32)
 // are forwarded from registers.  A pair with two equal samples is executed by worker 0 alone, one target after the
 // other.  Every floating-point operation and its order is the one of o2_ordered_d128_kernel: same bits.
 // Requires window <= 15 (a centre's window fits the 32 lanes of the scheduling warp) and disjoint node / ctx tables.
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 template <int ID, int NTHREADS>
 __device__ __forceinline__ void named_barrier() {
     asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory");
