@@ -87,8 +87,10 @@ class Community2Vec(object):
 def _rows_of(model, nodes):
     """[model.vocab[x].index for x in nodes] (community_embeddings.py:63) without a Python loop for integer ids; an id
     that is not in the vocabulary raises KeyError like the reference's dict lookup."""
+    if not isinstance(nodes, np.ndarray):
+        nodes = list(nodes)  # may be a one-shot iterator
     try:
-        a = np.asarray(nodes if isinstance(nodes, np.ndarray) else list(nodes))
+        a = np.asarray(nodes)
     except Exception:
         a = None
     if a is None or a.ndim != 1 or a.dtype.kind not in "iu" or a.size == 0 or not hasattr(model, "id_index"):

@@ -210,3 +210,32 @@ def test_paths_to_rows_rectangular_fast_paths_equal_the_per_path_loop():
             np.random.seed(5)
             f2, o2 = paths_to_rows(m, [list(r) for r in a])
             assert np.array_equal(f1, f2) and np.array_equal(o1, o2)
+
+
+def test_community2vec_row_lookup_matches_the_dict_loop():
+    """Community2Vec.train maps node ids to rows (community_embeddings.py:63): vectorised for integer ids, dict loop for
+    everything else; an unknown id raises KeyError like the reference's `model.vocab[x]`."""
+    from comemb_b200.ADSCModel.community_embeddings import _rows_of
+
+    class V(object):
+        def __init__(self, i):
+            self.index = i
+
+    class WithIndex(object):
+        def __init__(self):
+            self.vocab = {k: V(i) for i, k in enumerate([5, 3, 9, 1])}
+
+        def id_index(self):
+            ids = np.array(sorted(self.vocab))
+            return ids, np.array([self.vocab[k].index for k in ids]), None
+
+    class Plain(object):
+        def __init__(self):
+            self.vocab = {k: V(i) for i, k in enumerate([5, 3, 9, 1])}
+
+    for m in (WithIndex(), Plain()):
+        assert _rows_of(m, [9, 1, 5]).tolist() == [2, 3, 0]
+        assert _rows_of(m, np.array([3, 3])).tolist() == [1, 1]
+        assert _rows_of(m, iter([1, 9])).tolist() == [3, 2]
+        with pytest.raises(KeyError):
+            _rows_of(m, [9, 2])
