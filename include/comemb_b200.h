@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define COMEMB_ABI_VERSION 1
+#define COMEMB_ABI_VERSION 2
 
 #define COMEMB_TOKEN_NONE 0xFFFFFFFFu /* a `None` entry of a path (pyx:485-486) / padding of a short walk */
 
@@ -47,18 +47,33 @@ int comemb_init(void);
 /* copy of the sigmoid table as uploaded (host buffer of 1000 floats); for tests */
 int comemb_get_lut(float *h_lut1000);
 int comemb_abi_version(void);
-/* Hogwild work decomposition: centres_per_unit = 0 -> one warp per walk (the reference's per-thread granularity);
- * > 0 -> one warp per chunk of that many centres (needs max_walk_len; the chunk starts at the right position of the
- * walk's LCG stream).  blocks_per_sm % 100: resident CTAs per SM (0 = occupancy query).  blocks_per_sm / 100 selects an
- * experimental kernel variant: 0 default, 5 = L2 eviction-priority hints on the size-128 o2 kernel, 7 / 8 = ORDERED
- * mode at size 128 on a single warp with / without the software pipeline (default: scheduling warp + one worker warp
- * per target row for o2, pipelined single warp for o1; all give the same bits), 9 = force the generic kernels where
- * a size-128 specialisation exists (used by the tests to cover both).  Process-global state, not thread-safe: set it
- * before launching, from one thread. */
+/* ---- per-thread launch options ---------------------------------------------------------------------------------------------
+ * The reference entry points are called concurrently from worker threads (pyx:443, 493).  Everything that steers a launch
+ * besides its arguments lives in this struct; comemb_set_opts() stores a copy in THREAD-LOCAL storage and it applies to the
+ * launches the calling thread makes afterwards (NULL restores the defaults), so two threads -- or one thread per GPU -- never
+ * see each other's settings.  No entry point keeps process-global mutable state. */
+#define COMEMB_VARIANT_DEFAULT 0       /* the fastest kernel for the shape */
+#define COMEMB_VARIANT_L2_HINTS 5      /* size-128 Hogwild o2: L2 eviction-priority hints (experiment) */
+#define COMEMB_VARIANT_ROUND1 6        /* round-1 kernels: fp64-pipe top-1 o3, per-warp mma.sync fused pass */
+#define COMEMB_VARIANT_ORDERED_PIPE 7  /* ORDERED size 128 on one software-pipelined warp */
+#define COMEMB_VARIANT_ORDERED_PLAIN 8 /* ORDERED size 128 on one plain warp */
+#define COMEMB_VARIANT_GENERIC 9       /* the any-size kernels even where a size-128 specialisation exists (tests) */
+typedef struct comemb_opts {
+    int32_t centres_per_unit; /* Hogwild o2: 0 = one warp per walk (the reference's per-thread granularity); > 0 = one warp
+                                 per chunk of that many centres (needs max_walk_len; the chunk starts at the right position
+                                 of the walk's LCG stream) */
+    int32_t max_walk_len;
+    int32_t blocks_per_sm;    /* resident CTAs per SM (0 = occupancy query) */
+    int32_t variant;          /* COMEMB_VARIANT_* */
+    int64_t max_warps;        /* HOGWILD concurrency cap: at most this many walks/edges in flight (0 = fill the GPU).  The
+                                 reference's `workers` plays this role; the learners pass max(workers, n_rows/28) so that
+                                 the expected number of concurrent updates per row stays below ~1/4 on small graphs */
+} comemb_opts_t;
+int comemb_set_opts(const comemb_opts_t *opts);
+int comemb_get_opts(comemb_opts_t *out);
+/* Shorthands that edit the calling thread's options: blocks_per_sm % 100 = resident CTAs per SM, blocks_per_sm / 100 =
+ * COMEMB_VARIANT_*. */
 int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm);
-/* HOGWILD concurrency cap: at most `max_warps` walks/edges are processed at the same time (0 = fill the GPU).  The
- * reference's `workers` count plays this role; the learners set max(workers, n_rows/28) so that the expected number
- * of concurrent updates hitting one row stays below ~1/4 on small graphs (karate: 34 rows). */
 int comemb_set_max_warps(int64_t max_warps);
 const char *comemb_error_string(int code);
 

@@ -21,6 +21,8 @@ SIGNATURES = {
     "comemb_init": (_i32, []),
     "comemb_get_lut": (_i32, [_vp]),
     "comemb_abi_version": (_i32, []),
+    "comemb_set_opts": (_i32, [_vp]),
+    "comemb_get_opts": (_i32, [_vp]),
     "comemb_set_tuning": (_i32, [_i32, _i32, _i32]),
     "comemb_set_max_warps": (_i32, [_i64]),
     "comemb_error_string": (_c.c_char_p, [_i32]),
@@ -48,6 +50,16 @@ SIGNATURES = {
     "comemb_scale": (_i32, [_vp, _i64, _f32, _vp]),
     "comemb_o2_pos_loss": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp]),
 }
+
+
+class ComembOpts(ctypes.Structure):
+    """comemb_opts_t (include/comemb_b200.h): the calling thread's launch options."""
+    _fields_ = [("centres_per_unit", _i32), ("max_walk_len", _i32), ("blocks_per_sm", _i32), ("variant", _i32),
+                ("max_warps", _i64)]
+
+
+VARIANT_DEFAULT, VARIANT_L2_HINTS, VARIANT_ROUND1, VARIANT_ORDERED_PIPE, VARIANT_ORDERED_PLAIN, VARIANT_GENERIC = (
+    0, 5, 6, 7, 8, 9)
 
 
 class ComembError(RuntimeError):
@@ -95,6 +107,31 @@ def ensure_init():
             check(load().comemb_set_tuning(*[int(v) for v in tune.split(",")]))
         _inited_devices.add(dev)
     return 0
+
+
+def get_opts():
+    o = ComembOpts()
+    check(load().comemb_get_opts(ctypes.byref(o)))
+    return o
+
+
+class opts(object):
+    """with opts(max_warps=8, variant=VARIANT_GENERIC): ...  -- edits the calling thread's launch options for the block
+    and restores the previous ones afterwards."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.prev = get_opts()
+        new = ComembOpts.from_buffer_copy(self.prev)
+        for k, v in self.kw.items():
+            setattr(new, k, int(v))
+        check(load().comemb_set_opts(ctypes.byref(new)))
+        return new
+
+    def __exit__(self, *a):
+        check(load().comemb_set_opts(ctypes.byref(self.prev)))
 
 
 def ptr(t):

@@ -20,23 +20,15 @@ int launch_o1_hogwild(float *, int, const uint32_t *, int64_t, const uint64_t *,
                       const uint32_t *, uint32_t, int, float, bool, int64_t, cudaStream_t);
 int launch_sg_fused_hogwild(float *, float *, int, const uint32_t *, const int64_t *, int64_t, const int32_t *,
                             const uint64_t *, uint64_t, const uint32_t *, uint64_t, const float *, const float *,
-                            const float *, int, int, int, float, float, float, int, bool, cudaStream_t);
-void hogwild_set_tuning(int, int, int);
+                            const float *, int, int, int, float, float, float, int, bool, int64_t, const int32_t *,
+                            const float *, cudaStream_t);
 int launch_o2_hogwild_sharded(float *const *, float *const *, int, int64_t, int, const uint32_t *, const int64_t *, int64_t,
                               const uint64_t *, uint64_t, const uint32_t *, uint64_t, int, int, float, float, int64_t *,
                               cudaStream_t);
-void hogwild_set_max_warps(int64_t);
-extern bool g_force_generic_ordered;
-extern int g_ordered_variant;
-extern bool g_force_generic_fused;
-extern bool g_force_generic_o3;
-extern int64_t g_fused_n_rows;
 int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, int64_t, int, double, double, double,
                    const float *, const float *, const float *, int, int, cudaStream_t);
 int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const float *, const float *, const float *,
                     const int32_t *, const float *, int, double, float, int, cudaStream_t);
-extern const int32_t *g_fused_comm;
-extern const float *g_fused_weight;
 int launch_transpose_blocks(const float *, float *, int, int, cudaStream_t);
 int launch_scale(float *, int64_t, float, cudaStream_t);
 int launch_o2_pos_loss(const float *, const float *, int, const uint32_t *, const int64_t *, int64_t, int, double *,
@@ -51,7 +43,10 @@ namespace {
 constexpr int MAX_DEVICES = 64;
 float *g_lut_dev[MAX_DEVICES] = {nullptr};
 float g_host_lut[EXP_TABLE_SIZE];
+thread_local comemb_opts_t t_opts = {0, 0, 0, 0, 0};
 }  // namespace
+
+const comemb_opts_t &comemb_opts() { return t_opts; }
 
 int comemb_check_init() {
     int dev = -1;
@@ -108,19 +103,36 @@ int comemb_get_lut(float *h_lut1000) {
     return 0;
 }
 
+int comemb_set_opts(const comemb_opts_t *opts) {
+    if (!opts) {
+        t_opts = comemb_opts_t{0, 0, 0, 0, 0};
+        return 0;
+    }
+    if (opts->centres_per_unit < 0 || opts->max_walk_len < 0 || opts->blocks_per_sm < 0 || opts->variant < 0 ||
+        opts->max_warps < 0)
+        return COMEMB_E_ARG;
+    t_opts = *opts;
+    return 0;
+}
+
+int comemb_get_opts(comemb_opts_t *out) {
+    if (!out) return COMEMB_E_ARG;
+    *out = t_opts;
+    return 0;
+}
+
 int comemb_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm) {
     if (centres_per_unit < 0 || max_walk_len < 0 || blocks_per_sm < 0) return COMEMB_E_ARG;
-    hogwild_set_tuning(centres_per_unit, max_walk_len, blocks_per_sm);
-    g_force_generic_ordered = (blocks_per_sm / 100) == 9;
-    g_ordered_variant = ((blocks_per_sm / 100) == 7 || (blocks_per_sm / 100) == 8) ? blocks_per_sm / 100 : 0;
-    g_force_generic_fused = (blocks_per_sm / 100) == 9;
-    g_force_generic_o3 = (blocks_per_sm / 100) == 9;
+    t_opts.centres_per_unit = centres_per_unit;
+    t_opts.max_walk_len = max_walk_len;
+    t_opts.blocks_per_sm = blocks_per_sm % 100;
+    t_opts.variant = blocks_per_sm / 100;
     return 0;
 }
 
 int comemb_set_max_warps(int64_t max_warps) {
     if (max_warps < 0) return COMEMB_E_ARG;
-    hogwild_set_max_warps(max_warps);
+    t_opts.max_warps = max_warps;
     return 0;
 }
 
@@ -255,11 +267,11 @@ int comemb_sg_fused(float *d_node, float *d_negemb, int64_t n_rows, int size, co
         return launch_sg_fused_ordered(d_node, d_negemb, size, d_walks, d_walk_off, n_walks, d_reduced_windows, d_seeds,
                                        base_seed, d_table, table_len, d_mu, d_inv_cov, d_pi, K, window, negative, lr,
                                        lambda1, lambda2, is_node_embedding, !(flags & COMEMB_F_DOT_FLOAT), st);
-    g_fused_n_rows = n_rows;
     if (mode == COMEMB_MODE_HOGWILD)
         return launch_sg_fused_hogwild(d_node, d_negemb, size, d_walks, d_walk_off, n_walks, d_reduced_windows, d_seeds,
                                        base_seed, d_table, table_len, d_mu, d_inv_cov, d_pi, K, window, negative, lr,
-                                       lambda1, lambda2, is_node_embedding, (flags & COMEMB_F_ATOMIC) != 0, st);
+                                       lambda1, lambda2, is_node_embedding, (flags & COMEMB_F_ATOMIC) != 0, n_rows,
+                                       nullptr, nullptr, st);
     return COMEMB_E_ARG;
 }
 
@@ -287,15 +299,10 @@ int comemb_sg_fused_top1(float *d_node, float *d_negemb, int64_t n_rows, int siz
     if (!d_table || table_len == 0) return COMEMB_E_ARG;
     if (!d_seeds && !(flags & COMEMB_F_SEED_HASH)) return COMEMB_E_ARG;
     if (n_walks == 0) return 0;
-    g_fused_n_rows = n_rows;
-    g_fused_comm = d_comm;
-    g_fused_weight = d_weight;
-    const int e = launch_sg_fused_hogwild(d_node, d_negemb, size, d_walks, d_walk_off, n_walks, d_reduced_windows, d_seeds,
-                                          base_seed, d_table, table_len, d_mu, d_inv_cov, nullptr, K, window, negative, lr,
-                                          lambda1, lambda2, 0, (flags & COMEMB_F_ATOMIC) != 0, (cudaStream_t)stream);
-    g_fused_comm = nullptr;
-    g_fused_weight = nullptr;
-    return e;
+    return launch_sg_fused_hogwild(d_node, d_negemb, size, d_walks, d_walk_off, n_walks, d_reduced_windows, d_seeds,
+                                   base_seed, d_table, table_len, d_mu, d_inv_cov, nullptr, K, window, negative, lr,
+                                   lambda1, lambda2, 0, (flags & COMEMB_F_ATOMIC) != 0, n_rows, d_comm, d_weight,
+                                   (cudaStream_t)stream);
 }
 
 int comemb_walks_csr(const int64_t *d_rowptr, const uint32_t *d_col, int64_t n, int num_paths, int path_length,

@@ -167,3 +167,5 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 int comemb_check_init();  // COMEMB_E_NOINIT unless comemb_init() ran on the current device
+// the calling thread's launch options (comemb_set_opts; thread-local, defaults all zero)
+const comemb_opts_t &comemb_opts();

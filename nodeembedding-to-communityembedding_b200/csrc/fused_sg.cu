@@ -14,11 +14,6 @@
 // fused pass is bound by the o3 term (FP64-FMA / L2), not by HBM.
 #include "comemb_common.cuh"
 
-int64_t hogwild_get_max_warps();
-extern int64_t g_fused_n_rows;
-extern bool g_force_generic_fused;
-extern const int32_t *g_fused_comm;
-extern const float *g_fused_weight;
 
 namespace {
 
@@ -551,8 +546,8 @@ int launch_t(const SgParams &P, bool atomic, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = (P.n_walks + WARPS - 1) / WARPS;
     int64_t cap = (int64_t)sms * 4;
-    if (hogwild_get_max_warps() > 0 && (hogwild_get_max_warps() + WARPS - 1) / WARPS < cap)
-        cap = (hogwild_get_max_warps() + WARPS - 1) / WARPS;
+    if (comemb_opts().max_warps > 0 && (comemb_opts().max_warps + WARPS - 1) / WARPS < cap)
+        cap = (comemb_opts().max_warps + WARPS - 1) / WARPS;
     const int grid = (int)(want < cap ? want : cap);
     const size_t smem = (EXP_TABLE_SIZE + (size_t)WARPS * P.d) * sizeof(float);
     if (atomic)
@@ -573,8 +568,8 @@ int launch_fast_t(const SgFastParams &F, bool atomic, cudaStream_t st) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FW * 32, smem);
         if (per_sm < 1) per_sm = 1;
         int64_t cap = (int64_t)sms * per_sm;
-        if (hogwild_get_max_warps() > 0 && (hogwild_get_max_warps() + FW - 1) / FW < cap)
-            cap = (hogwild_get_max_warps() + FW - 1) / FW;
+        if (comemb_opts().max_warps > 0 && (comemb_opts().max_warps + FW - 1) / FW < cap)
+            cap = (comemb_opts().max_warps + FW - 1) / FW;
         const int64_t want = (F.n_walks + FW - 1) / FW;
         kernel<<<(int)(want < cap ? want : cap), FW * 32, smem, st>>>(F);
         return (int)cudaGetLastError();
@@ -592,16 +587,14 @@ int launch_fast(const SgFastParams &F, int negative, bool atomic, cudaStream_t s
 
 }  // namespace
 
-int64_t g_fused_n_rows = 0;           // set by comemb_sg_fused (the one-hot scan needs the row count of pi)
-const int32_t *g_fused_comm = nullptr;  // comemb_sg_fused_top1: caller-provided top-1 form of pi (no dense pi at all)
-const float *g_fused_weight = nullptr;
-bool g_force_generic_fused = false;   // tests: comemb_set_tuning(.., .., 900)
-
 int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t *walks, const int64_t *walk_off,
                             int64_t n_walks, const int32_t *reduced_windows, const uint64_t *seeds, uint64_t base_seed,
                             const uint32_t *table, uint64_t table_len, const float *mu, const float *inv_cov,
                             const float *pi, int K, int window, int negative, float lr, float lambda1, float lambda2,
-                            int is_node_embedding, bool atomic, cudaStream_t st) {
+                            int is_node_embedding, bool atomic, int64_t n_rows, const int32_t *top1_comm,
+                            const float *top1_weight, cudaStream_t st) {
+    // n_rows: rows of pi (the one-hot scan).  top1_comm / top1_weight: pi in top-1 form supplied by the caller
+    // (comemb_sg_fused_top1; no dense pi then).
     if (size > 512) return COMEMB_E_UNSUPPORTED;
     if (n_walks == 0) return 0;
     SgParams P;
@@ -611,15 +604,14 @@ int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t
     P.lr = lr; P.lambda1 = lambda1; P.lambda2 = lambda2; P.is_node_embedding = is_node_embedding;
     P.glut = comemb_lut_device();
     // fast path: size 128, NEG in {3,4,5}, separate context table, window <= 12, pi one-hot (or lambda2 == 0)
-    const bool top1 = g_fused_comm != nullptr;  // the caller already holds pi in top-1 form (and no dense pi)
+    const bool top1 = top1_comm != nullptr;  // the caller already holds pi in top-1 form (and no dense pi)
     if (size == 128 && !is_node_embedding && negemb != node && 2 * window <= VMAX && negative >= 3 && negative <= 5 &&
-        (!g_force_generic_fused || top1)) {
+        (comemb_opts().variant != COMEMB_VARIANT_GENERIC || top1)) {
         int32_t *comm = nullptr;
         float *weight = nullptr;
         bool ok = true;
         if (lambda2 != 0.f && !top1) {
             int *flag = nullptr, h_flag = 0;
-            const int64_t n_rows = g_fused_n_rows;
             if (n_rows <= 0) ok = false;
             if (ok) {
                 CUDA_TRY(cudaMallocAsync(&comm, (size_t)n_rows * sizeof(int32_t), st));
@@ -644,7 +636,7 @@ int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t
             F.node = node; F.ctx = negemb; F.walks = walks; F.walk_off = walk_off; F.n_walks = n_walks;
             F.rw = reduced_windows; F.seeds = seeds; F.base_seed = base_seed; F.table = table; F.mod = P.mod;
             F.mu = mu; F.inv_cov = inv_r ? inv_r : inv_cov;
-            F.comm = top1 ? g_fused_comm : comm; F.weight = top1 ? g_fused_weight : weight; F.window = window;
+            F.comm = top1 ? top1_comm : comm; F.weight = top1 ? top1_weight : weight; F.window = window;
             F.lr = lr; F.lambda1 = lambda1; F.lambda2 = lambda2; F.glut = P.glut;
             const int e = launch_fast(F, negative, atomic, st);
             if (inv_r) CUDA_TRY(cudaFreeAsync(inv_r, st));

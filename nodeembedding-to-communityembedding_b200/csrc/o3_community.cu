@@ -16,7 +16,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
-bool g_force_generic_o3 = false;  // tests: comemb_set_tuning(.., .., 900) keeps the one-row-per-warp kernel
+int launch_o3_gemm(float *, const uint32_t *, int64_t, const float *, const float *, const int32_t *, const float *, int,
+                   float, float, int, cudaStream_t);
 
 namespace {
 
@@ -271,7 +272,13 @@ int launch_o3_batch(float *node, int64_t n_rows, int size, const uint32_t *rows,
     int64_t want = (n_sel + O3_WARPS - 1) / O3_WARPS;
     int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     size_t smem = (size_t)O3_WARPS * size * sizeof(float);
-    if (!pi && size == 128 && !g_force_generic_o3 && n_sel >= 4 * O3F_T && n_sel < (1LL << 31) && K < (1 << 30)) {
+    const int variant = comemb_opts().variant;
+    if (!pi && size == 128 && variant != COMEMB_VARIANT_GENERIC && variant != COMEMB_VARIANT_ROUND1) {
+        // top-1 form at the headline size: grouped GEMM on the tensor cores (o3_gemm.cu)
+        const int r = launch_o3_gemm(node, rows, n_sel, mu, inv_cov_t, comm, weight, K, scale, lr, iters, st);
+        if (r != COMEMB_E_UNSUPPORTED) return r;
+    }
+    if (!pi && size == 128 && variant != COMEMB_VARIANT_GENERIC && n_sel >= 4 * O3F_T && n_sel < (1LL << 31) && K < (1 << 30)) {
         // top-1 form at the headline size: group the rows by community, 8 rows per warp (o3_top1_d128_kernel); rows
         // without a community or with a weight != 1 keep the one-row-per-warp kernel.
         uint32_t *buf = nullptr;

@@ -1,0 +1,282 @@
+// o3_gemm.cu -- the community gradient step (Community2Vec.train, ADSCModel/community_embeddings.py:61-77) at size 128
+// with pi in top-1 form, as a grouped GEMM on the 5th-generation tensor cores:
+//
+//   rows are bucketed by community (histogram + scan + scatter, three small kernels); a tile job is (community c,
+//   up to TN rows of it).  A persistent CTA per SM walks a contiguous range of jobs; for each it
+//     * keeps inv_cov_c resident in shared memory as the tcgen05 A operand (hi/lo TF32 images, 128 KB, fetched by
+//       the TMA engine with cp.async.bulk only when the community changes),
+//     * gathers the rows, forms diff = x - mu_c, splits it into hi/lo TF32 and stores the swizzled B operand,
+//     * one elected thread issues 48 tcgen05.mma (3xTF32, see umma.cuh) with the accumulator in TMEM,
+//     * all warps read the accumulator back (tcgen05.ld) and apply  x -= clip(w * G * (beta/K), +-5) * lr.
+//
+// Accuracy: 3xTF32 products with fp32 accumulation -- the same fp32-level result as the reference's numpy matmul up to
+// summation order (tests: <= 1e-5 against the reference's golden output; the previous CUDA-core kernel mirrored the
+// ORACLE's double-accumulated dot bit for bit, which the reference itself does not do).
+#include "comemb_common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int D = 128;
+constexpr int A_IMG_BYTES = 2 * D * D * 4;  // hi + lo images of one community: 128 KB
+
+// ---- operand preparation: P [K][128][128] fp32 -> per community {hi image, lo image} with A[m][k] = P[c][k][m] --------------
+// (o3 HEAD passes inv_cov with its blocks transposed, and G = inv_cov . diff needs A[m][k] = inv_cov[m][k] = P[k][m];
+//  the fused pass passes inv_cov itself and needs Y = inv_cov^T . diff, again A[m][k] = P[k][m].)
+__global__ void umma_prep_a_kernel(const float *__restrict__ P, char *__restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i >> 14;
+        const int k = (int)((i >> 7) & 127), m = (int)(i & 127);  // consecutive threads read consecutive m: coalesced
+        const float v = P[i];
+        const float hi = umma::tf32_round(v);
+        const float lo = umma::tf32_round(v - hi);
+        char *img = out + c * A_IMG_BYTES;
+        const uint32_t off = umma::sw128_offset(D, m, k);
+        *reinterpret_cast<float *>(img + off) = hi;
+        *reinterpret_cast<float *>(img + D * D * 4 + off) = lo;
+    }
+}
+
+// ---- bucketing rows by community ---------------------------------------------------------------------------------------------
+__global__ void o3g_count_kernel(const uint32_t *rows, int64_t n_sel, const int32_t *comm, const float *weight, int K,
+                                 int *count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_sel; s += stride) {
+        const uint32_t r = rows ? rows[s] : (uint32_t)s;
+        const int c = comm[r];
+        if (c >= 0 && c < K && weight[r] != 0.f) atomicAdd(count + c, 1);
+    }
+}
+
+// one block: exclusive scan of the K counts -> row cursor per community, and the tile job list
+template <int TN>
+__global__ void o3g_scan_kernel(const int *count, int K, int *cursor, int4 *jobs, int *n_jobs) {
+    __shared__ int s_row[1024], s_tile[1024];
+    __shared__ int carry_row, carry_tile;
+    if (threadIdx.x == 0) carry_row = carry_tile = 0;
+    __syncthreads();
+    for (int base = 0; base < K; base += 1024) {
+        const int c = base + threadIdx.x;
+        const int n = c < K ? count[c] : 0, t = (n + TN - 1) / TN;
+        s_row[threadIdx.x] = n;
+        s_tile[threadIdx.x] = t;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+            const int a = threadIdx.x >= o ? s_row[threadIdx.x - o] : 0, b = threadIdx.x >= o ? s_tile[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_row[threadIdx.x] += a;
+            s_tile[threadIdx.x] += b;
+            __syncthreads();
+        }
+        const int row0 = carry_row + s_row[threadIdx.x] - n, tile0 = carry_tile + s_tile[threadIdx.x] - t;
+        if (c < K) {
+            cursor[c] = row0;
+            for (int q = 0; q < t; q++) jobs[tile0 + q] = make_int4(c, row0 + q * TN, min(TN, n - q * TN), 0);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            carry_row += s_row[1023];
+            carry_tile += s_tile[1023];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_jobs = carry_tile;
+}
+
+__global__ void o3g_scatter_kernel(const uint32_t *rows, int64_t n_sel, const int32_t *comm, const float *weight, int K,
+                                   int *cursor, uint32_t *srows) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_sel; s += stride) {
+        const uint32_t r = rows ? rows[s] : (uint32_t)s;
+        const int c = comm[r];
+        if (c >= 0 && c < K && weight[r] != 0.f) srows[atomicAdd(cursor + c, 1)] = r;
+    }
+}
+
+// ---- the grouped GEMM ------------------------------------------------------------------------------------------------------------
+struct O3GemmParams {
+    float *node;
+    const uint32_t *srows;
+    const int4 *jobs;
+    const int *n_jobs;
+    const float *mu;
+    const char *a_img;
+    const float *weight;
+    float scale, lr;
+    int iters;
+};
+
+template <int TN>
+struct O3GemmSmem {
+    static constexpr int A_HI = 0, A_LO = D * D * 4, B_HI = 2 * D * D * 4, B_LO = B_HI + TN * D * 4;
+    static constexpr int MU = B_LO + TN * D * 4, ROW = MU + D * 4, WGT = ROW + TN * 4, BAR = WGT + TN * 4;
+    static constexpr int TOTAL = BAR + 32;
+};
+
+template <int TN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmParams P) {
+    using L = O3GemmSmem<TN>;
+    static_assert(TN % 16 == 0 && TN <= 256 && WARPS % 4 == 0, "tile shape");
+    constexpr uint32_t TMEM_COLS = TN <= 32 ? 32 : TN <= 64 ? 64 : TN <= 128 ? 128 : 256;
+    extern __shared__ char smem_raw[];
+    char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *mu_s = reinterpret_cast<float *>(smem + L::MU);
+    uint32_t *row_s = reinterpret_cast<uint32_t *>(smem + L::ROW);
+    float *wgt_s = reinterpret_cast<float *>(smem + L::WGT);
+    uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (warp == 0) umma::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x == 0) {
+        umma::mbar_init(bar_a, 1);
+        umma::mbar_init(bar_mma, 1);
+        umma::fence_mbar_init();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t taddr = *tmem_slot;
+    const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
+    const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
+
+    const int n_jobs = *P.n_jobs;
+    const int j0 = (int)((int64_t)n_jobs * blockIdx.x / gridDim.x), j1 = (int)((int64_t)n_jobs * (blockIdx.x + 1) / gridDim.x);
+    int cur_c = -1;
+    uint32_t par_a = 0, par_m = 0;
+    bool a_pending = false;
+    for (int j = j0; j < j1; j++) {
+        const int4 job = P.jobs[j];
+        const int c = job.x, start = job.y, cnt = job.z;
+        const int n16 = (cnt + 15) & ~15;
+        if (c != cur_c) {  // every MMA that read the resident A has completed (bar_mma was waited on below)
+            if (threadIdx.x == 0) {
+                umma::mbar_expect_tx(bar_a, A_IMG_BYTES);
+                const char *src = P.a_img + (int64_t)c * A_IMG_BYTES;
+#pragma unroll
+                for (int q = 0; q < 8; q++) umma::bulk_g2s(smem + L::A_HI + q * 16384, src + q * 16384, 16384, bar_a);
+            }
+            if (warp == 1) *reinterpret_cast<float4 *>(mu_s + 4 * lane) =
+                __ldg(reinterpret_cast<const float4 *>(P.mu + (int64_t)c * D + 4 * lane));
+            a_pending = true;
+            cur_c = c;
+            __syncthreads();  // mu_s visible
+        }
+        for (int it = 0; it < P.iters; it++) {
+            // ---- B operand: diff rows, hi/lo split, swizzled K-major ----------------------------------------------------
+            const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
+            for (int r = warp; r < cnt; r += WARPS) {
+                const uint32_t row = __ldg(P.srows + start + r);
+                const float4 x = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row * D + 4 * lane));
+                const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+                const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y), umma::tf32_round(df.z),
+                                              umma::tf32_round(df.w));
+                const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
+                                              umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
+                const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
+                *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
+                *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
+                if (it == 0 && lane == 0) {
+                    row_s[r] = row;
+                    wgt_s[r] = __ldg(P.weight + row);
+                }
+            }
+            umma::fence_proxy_async_smem();
+            __syncthreads();
+            if (warp == 0) {
+                if (a_pending) {
+                    umma::mbar_wait(bar_a, par_a);
+                    par_a ^= 1;
+                }
+                umma::tc_fence_after();
+                if (lane == 0) {
+                    umma::issue_3xtf32(taddr, a_hi, a_lo, b_hi, b_lo, TN, n16);
+                    umma::mma_commit(bar_mma);
+                }
+                __syncwarp();
+            }
+            a_pending = false;
+            umma::mbar_wait(bar_mma, par_m);
+            par_m ^= 1;
+            umma::tc_fence_after();
+            // ---- epilogue: thread = output coordinate a of TMEM lane quarter (warp % 4), 16 rows at a time ----------------
+            const int a = 32 * (warp & 3) + lane;
+            for (int ch = warp >> 2; ch * 16 < n16; ch += WARPS / 4) {
+                float v[16];
+                umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ch * 16), v);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int n = ch * 16 + q;
+                    if (n < cnt) {
+                        float *xp = P.node + (int64_t)row_s[n] * D + a;
+                        float g = __fmul_rn(__fmul_rn(wgt_s[n], v[q]), P.scale);  // :71, :76
+                        g = fminf(fmaxf(g, -5.f), 5.f);                           // :77
+                        *xp = __ldcg(xp) - __fmul_rn(g, P.lr);
+                    }
+                }
+            }
+            umma::tc_fence_before();
+            __threadfence_block();
+            __syncthreads();  // accumulator and B images are free again; the updated rows are visible to the CTA
+        }
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(taddr, TMEM_COLS);
+}
+
+}  // namespace
+
+// P: [K][128][128] fp32; out: K * 128 KB operand images (see umma_prep_a_kernel)
+int launch_umma_prep_a(const float *P, char *out, int K, cudaStream_t st) {
+    const int64_t n = (int64_t)K * D * D;
+    if (n <= 0) return 0;
+    umma_prep_a_kernel<<<(unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8), 256, 0, st>>>(P, out, n);
+    return (int)cudaGetLastError();
+}
+
+// top-1 form at size 128; returns COMEMB_E_UNSUPPORTED when the shape does not fit (the caller falls back)
+int launch_o3_gemm(float *node, const uint32_t *rows, int64_t n_sel, const float *mu, const float *inv_cov_t,
+                   const int32_t *comm, const float *weight, int K, float scale, float lr, int iters, cudaStream_t st) {
+    constexpr int TN = 64, WARPS = 8;
+    using L = O3GemmSmem<TN>;
+    if (n_sel <= 0 || iters <= 0) return 0;
+    if (n_sel >= (1LL << 31) || K > (1 << 20)) return COMEMB_E_UNSUPPORTED;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t max_jobs = (n_sel + TN - 1) / TN + K;
+    char *scratch = nullptr;
+    const size_t off_count = 0, off_cursor = off_count + (size_t)K * 4, off_njobs = off_cursor + (size_t)K * 4;
+    const size_t off_jobs = (off_njobs + 4 + 15) & ~(size_t)15, off_srows = off_jobs + (size_t)max_jobs * 16;
+    const size_t off_img = (off_srows + (size_t)n_sel * 4 + 1023) & ~(size_t)1023;
+    const size_t total = off_img + (size_t)K * A_IMG_BYTES;
+    CUDA_TRY(cudaMallocAsync(&scratch, total, st));
+    auto fail = [&](cudaError_t e) {
+        cudaFreeAsync(scratch, st);
+        return (int)e;
+    };
+    int *count = reinterpret_cast<int *>(scratch + off_count), *cursor = reinterpret_cast<int *>(scratch + off_cursor);
+    int *n_jobs = reinterpret_cast<int *>(scratch + off_njobs);
+    int4 *jobs = reinterpret_cast<int4 *>(scratch + off_jobs);
+    uint32_t *srows = reinterpret_cast<uint32_t *>(scratch + off_srows);
+    char *img = scratch + off_img;
+    cudaError_t e = cudaMemsetAsync(count, 0, (size_t)K * 4, st);
+    if (e != cudaSuccess) return fail(e);
+    const int g1 = (int)((n_sel + 255) / 256 < sms * 8 ? (n_sel + 255) / 256 : sms * 8);
+    o3g_count_kernel<<<g1, 256, 0, st>>>(rows, n_sel, comm, weight, K, count);
+    o3g_scan_kernel<TN><<<1, 1024, 0, st>>>(count, K, cursor, jobs, n_jobs);
+    o3g_scatter_kernel<<<g1, 256, 0, st>>>(rows, n_sel, comm, weight, K, cursor, srows);
+    int r = launch_umma_prep_a(inv_cov_t, img, K, st);
+    if (r) return fail((cudaError_t)r);
+    O3GemmParams P;
+    P.node = node; P.srows = srows; P.jobs = jobs; P.n_jobs = n_jobs; P.mu = mu; P.a_img = img; P.weight = weight;
+    P.scale = scale; P.lr = lr; P.iters = iters;
+    const int smem = L::TOTAL + 1024;
+    e = cudaFuncSetAttribute(o3_gemm_kernel<TN, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(e);
+    const int grid = (int)(max_jobs < sms ? max_jobs : sms);
+    o3_gemm_kernel<TN, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
+    e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    return (int)e;
+}

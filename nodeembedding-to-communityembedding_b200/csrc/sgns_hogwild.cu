@@ -18,14 +18,6 @@ namespace {
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int NEGB = 5;  // negatives gathered per batch (neg=5 -> one batch)
 
-struct Tuning {
-    int centres_per_unit = 0;  // 0 = a whole walk per warp
-    int max_walk_len = 0;      // needed when centres_per_unit > 0
-    int blocks_per_sm = 0;     // 0 = occupancy query
-    int64_t max_warps = 0;     // 0 = fill the GPU; else cap on concurrently running walks/edges (Hogwild staleness)
-    int variant = 0;           // d=128 o2 kernel: 3 -> 80-register build (3 CTAs/SM), else 64-register build (4 CTAs/SM)
-};
-Tuning g_tuning;
 
 template <int NCH>
 struct Row {
@@ -720,12 +712,12 @@ int grid_for(K kernel, int64_t n_units, size_t dyn_smem = 0) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS_PER_BLOCK * 32, dyn_smem);
-    if (g_tuning.blocks_per_sm > 0) per_sm = g_tuning.blocks_per_sm;
+    if (comemb_opts().blocks_per_sm > 0) per_sm = comemb_opts().blocks_per_sm;
     if (per_sm < 1) per_sm = 1;
     int64_t want = (n_units + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     int64_t cap = (int64_t)sms * per_sm;  // a multiple of the SM count: every SM holds its full complement of warps
-    if (g_tuning.max_warps > 0) {
-        const int64_t lim = (g_tuning.max_warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    if (comemb_opts().max_warps > 0) {
+        const int64_t lim = (comemb_opts().max_warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         if (lim < cap) cap = lim;
     }
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
@@ -747,7 +739,7 @@ int launch_o2_t(const O2Params &P, bool atomic, cudaStream_t st) {
 template <int NEG>
 int launch_o2_d128(const O2Params &P, bool atomic, cudaStream_t st) {
     const int64_t n_units = P.n_walks * P.units_per_walk;
-    const bool hint = g_tuning.variant == 5;  // experiment: L2 eviction-priority hints
+    const bool hint = comemb_opts().variant == COMEMB_VARIANT_L2_HINTS;  // experiment: L2 eviction-priority hints
 #define COMEMB_LAUNCH(ATOM, HINT)                                            \
     do {                                                                     \
         auto k = o2_hogwild_d128_kernel<ATOM, NEG, 3, HINT, false>;          \
@@ -781,16 +773,6 @@ int launch_o1_t(const O1Params &P, bool atomic, cudaStream_t st) {
 
 }  // namespace
 
-void hogwild_set_max_warps(int64_t max_warps) { g_tuning.max_warps = max_warps; }
-int64_t hogwild_get_max_warps() { return g_tuning.max_warps; }
-
-void hogwild_set_tuning(int centres_per_unit, int max_walk_len, int blocks_per_sm) {
-    g_tuning.centres_per_unit = centres_per_unit;
-    g_tuning.max_walk_len = max_walk_len;
-    g_tuning.blocks_per_sm = blocks_per_sm % 100;
-    g_tuning.variant = blocks_per_sm / 100;  // hundreds digit selects the kernel variant (experiments)
-}
-
 int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, const int64_t *walk_off,
                       int64_t n_walks, const uint64_t *seeds, uint64_t base_seed, const uint32_t *table,
                       uint64_t table_len, const uint32_t *alias, uint32_t n_alias, int window, int negative, float lr,
@@ -803,16 +785,16 @@ int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, 
     P.draw = Draw{table, make_table_mod(table_len), alias, n_alias};
     P.window = window; P.negative = negative; P.lr = lr; P.lambda = lambda;
     P.centres_per_unit = 0; P.units_per_walk = 1;
-    if (g_tuning.centres_per_unit > 0 && g_tuning.max_walk_len > 0) {
-        P.centres_per_unit = g_tuning.centres_per_unit;
-        P.units_per_walk = (g_tuning.max_walk_len + P.centres_per_unit - 1) / P.centres_per_unit;
+    if (comemb_opts().centres_per_unit > 0 && comemb_opts().max_walk_len > 0) {
+        P.centres_per_unit = comemb_opts().centres_per_unit;
+        P.units_per_walk = (comemb_opts().max_walk_len + P.centres_per_unit - 1) / P.centres_per_unit;
     }
     P.n_tokens = n_tokens;
     P.glut = comemb_lut_device();
     P.n_shards = 0;
     P.rows_per_shard = 1;
     const bool vec = (size % 4) == 0;
-    if (size == 128 && g_tuning.variant != 9) {  // the headline shape (variant 9 forces the generic kernel: tests)
+    if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC) {  // the headline shape (variant 9 forces the generic kernel: tests)
         switch (negative) {
             case 1: return launch_o2_d128<1>(P, atomic, st);
             case 2: return launch_o2_d128<2>(P, atomic, st);
@@ -841,7 +823,7 @@ int launch_o1_hogwild(float *node, int size, const uint32_t *edges, int64_t n_ed
     P.negative = negative; P.lr = lr; P.stride = stride > 1 ? stride % n_edges : 0;
     P.glut = comemb_lut_device();
     const bool vec = (size % 4) == 0;
-    if (size == 128 && g_tuning.variant != 9) {
+    if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC) {
 #define COMEMB_O1(N)                                                                  \
     case N:                                                                           \
         if (atomic) {                                                                 \

@@ -16,10 +16,9 @@
 //   o2_ordered_d128_team_kernel (default for o2, window <= 15)      scheduling warp + one worker warp per target row
 // They all produce the same bits (tests/test_gpu_parity.py::test_o2_ordered_d128_kernel_variants_hazards).
 #include "comemb_common.cuh"
-
-bool g_force_generic_ordered = false;  // tests: comemb_set_tuning(.., .., 900) routes size 128 to the generic kernels
-int g_ordered_variant = 0;  // comemb_set_tuning(.., .., 100*v): size-128 ORDERED kernels -- 0: one warp per target row (o2) /
-                            // pipelined (o1); 7: single warp, software-pipelined; 8: single warp, plain
+// comemb_opts().variant selects among the size-128 ORDERED kernels: default = one worker warp per target row (o2) /
+// pipelined single warp (o1); ORDERED_PIPE = single warp, software-pipelined; ORDERED_PLAIN = single warp, plain;
+// GENERIC = the any-size kernels.
 
 namespace {
 
@@ -1160,7 +1159,7 @@ int launch_o2_ordered(float *node, float *ctx, int64_t n_rows, int size, const u
                       cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
     const bool disjoint = node + n_rows * size <= ctx || ctx + n_rows * size <= node;
-    if (size == 128 && !g_force_generic_ordered && disjoint && g_ordered_variant == 0 &&
+    if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC && disjoint && !(comemb_opts().variant == COMEMB_VARIANT_ORDERED_PIPE || comemb_opts().variant == COMEMB_VARIANT_ORDERED_PLAIN) &&
         window <= TEAM_MAX_WINDOW) {  // warp per target row + scheduling warp, same bits
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                             \
@@ -1174,7 +1173,7 @@ int launch_o2_ordered(float *node, float *ctx, int64_t n_rows, int size, const u
             default: break;
         }
     }
-    if (size == 128 && !g_force_generic_ordered && disjoint && g_ordered_variant != 8) {  // pipelined single warp
+    if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC && disjoint && comemb_opts().variant != COMEMB_VARIANT_ORDERED_PLAIN) {  // pipelined single warp
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                             \
     case N:                                                                                                        \
@@ -1188,7 +1187,7 @@ int launch_o2_ordered(float *node, float *ctx, int64_t n_rows, int size, const u
             default: break;
         }
     }
-    if (size == 128 && !g_force_generic_ordered) {  // register-resident fast path, same bits
+    if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC) {  // register-resident fast path, same bits
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                             \
     case N:                                                                                                        \
@@ -1212,7 +1211,7 @@ int launch_o1_ordered(float *node, int size, const uint32_t *edges, int64_t n_ed
                       uint64_t base_seed, const uint32_t *table, uint64_t table_len, int negative, float lr, bool quirk,
                       cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
-    if (size == 128 && !g_force_generic_ordered && g_ordered_variant != 8) {  // pipelined fast path, same bits
+    if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC && comemb_opts().variant != COMEMB_VARIANT_ORDERED_PLAIN) {  // pipelined fast path, same bits
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                              \
     case N:                                                                                                         \
@@ -1224,7 +1223,7 @@ int launch_o1_ordered(float *node, int size, const uint32_t *edges, int64_t n_ed
             default: break;
         }
     }
-    if (size == 128 && !g_force_generic_ordered) {  // register-resident fast path, same bits
+    if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC) {  // register-resident fast path, same bits
         switch (negative) {
 #define COMEMB_CASE(N)                                                                                              \
     case N:                                                                                                         \

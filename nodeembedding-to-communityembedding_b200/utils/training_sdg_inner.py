@@ -149,16 +149,20 @@ def hogwild_concurrency(n_rows, workers=1):
 
 
 class _max_warps(object):
+    """Concurrency cap for the launches inside the block; the caller's previous cap is restored afterwards."""
+
     def __init__(self, n):
         self.n = n
+        self.ctx = None
 
     def __enter__(self):
         if self.n:
-            _lib.check(_lib.load().comemb_set_max_warps(int(self.n)))
+            self.ctx = _lib.opts(max_warps=int(self.n))
+            self.ctx.__enter__()
 
     def __exit__(self, *a):
-        if self.n:
-            _lib.check(_lib.load().comemb_set_max_warps(0))
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def o2_batch(node, ctx, walks, walk_off, seeds, lr, negative, window, table, alpha=1.0, mode=MODE_ORDERED, flags=0,

@@ -24,8 +24,41 @@ def test_capi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.comemb_abi_version() == 1
+    assert lib.comemb_abi_version() == 2
     assert b"invalid argument" in lib.comemb_error_string(-1)
+
+
+def test_launch_options_are_per_thread_and_restored():
+    """comemb_opts_t lives in thread-local storage (no CUDA call involved): a worker thread's settings never leak into
+    another thread, `_lib.opts(...)` restores what was there before, and invalid values are refused."""
+    import ctypes
+    import threading
+    from comemb_b200 import _lib
+    lib = _lib.load()
+    assert lib.comemb_set_opts(None) == 0
+    with _lib.opts(max_warps=7):
+        assert _lib.get_opts().max_warps == 7
+        seen = {}
+
+        def other():
+            seen["before"] = _lib.get_opts().max_warps
+            with _lib.opts(max_warps=3, variant=_lib.VARIANT_GENERIC):
+                seen["inside"] = (_lib.get_opts().max_warps, _lib.get_opts().variant)
+        t = threading.Thread(target=other)
+        t.start()
+        t.join()
+        assert seen == {"before": 0, "inside": (3, 9)}
+        with _lib.opts(variant=_lib.VARIANT_ROUND1):
+            o = _lib.get_opts()
+            assert (o.max_warps, o.variant) == (7, 6)
+        assert _lib.get_opts().variant == 0 and _lib.get_opts().max_warps == 7
+    assert _lib.get_opts().max_warps == 0
+    assert lib.comemb_set_tuning(4, 80, 903) == 0
+    o = _lib.get_opts()
+    assert (o.centres_per_unit, o.max_walk_len, o.blocks_per_sm, o.variant) == (4, 80, 3, 9)
+    bad = _lib.ComembOpts(0, 0, 0, 0, -1)
+    assert lib.comemb_set_opts(ctypes.byref(bad)) == -1
+    assert lib.comemb_set_opts(None) == 0 and _lib.get_opts().variant == 0
 
 
 def test_product_never_imports_the_oracle():
