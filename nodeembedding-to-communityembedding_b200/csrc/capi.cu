@@ -292,9 +292,9 @@ int comemb_sg_fused_top1(float *d_node, float *d_negemb, int64_t n_rows, int siz
                          const float *d_mu, const float *d_inv_cov, const int32_t *d_comm, const float *d_weight, int K,
                          int window, int negative, float lr, float lambda1, float lambda2, uint32_t flags, void *stream) {
     REQUIRE_INIT();
-    if (!d_node || !d_negemb || d_node == d_negemb || n_rows <= 0 || size != 128 || n_walks < 0 || window < 0 ||
-        2 * window > 24 || negative < 3 || negative > 5 || !d_comm || !d_weight || !d_mu || !d_inv_cov || K <= 0)
-        return COMEMB_E_UNSUPPORTED;  // this entry exists for the tensor-core kernel only
+    if (!d_node || !d_negemb || d_node == d_negemb || n_rows <= 0 || size != 128 || n_walks < 0 || window < 1 ||
+        2 * window > 64 || negative < 1 || negative > 7 || !d_comm || !d_weight || !d_mu || !d_inv_cov || K <= 0)
+        return COMEMB_E_UNSUPPORTED;  // this entry exists for the tensor-core kernels only
     if (n_walks > 0 && (!d_walks || !d_walk_off)) return COMEMB_E_ARG;
     if (!d_table || table_len == 0) return COMEMB_E_ARG;
     if (!d_seeds && !(flags & COMEMB_F_SEED_HASH)) return COMEMB_E_ARG;

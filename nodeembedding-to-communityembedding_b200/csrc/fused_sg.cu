@@ -15,6 +15,10 @@
 #include "comemb_common.cuh"
 
 
+int launch_sg_fused_round(float *, float *, const uint32_t *, const int64_t *, int64_t, const int32_t *, const uint64_t *,
+                          uint64_t, const uint32_t *, uint64_t, const float *, const float *, const float *, int, int, int,
+                          float, float, float, int, bool, int64_t, const int32_t *, const float *, cudaStream_t);
+
 namespace {
 
 constexpr int WARPS = 8;
@@ -603,8 +607,16 @@ int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t
     P.mu = mu; P.inv_cov = inv_cov; P.pi = pi; P.K = K; P.window = window; P.negative = negative;
     P.lr = lr; P.lambda1 = lambda1; P.lambda2 = lambda2; P.is_node_embedding = is_node_embedding;
     P.glut = comemb_lut_device();
-    // fast path: size 128, NEG in {3,4,5}, separate context table, window <= 12, pi one-hot (or lambda2 == 0)
     const bool top1 = top1_comm != nullptr;  // the caller already holds pi in top-1 form (and no dense pi)
+    const int variant = comemb_opts().variant;
+    if (size == 128 && (variant == COMEMB_VARIANT_DEFAULT || variant == COMEMB_VARIANT_TENSOR)) {
+        // the round-synchronous kernel with the o3 half on tcgen05 (fused_round.cu): any pi, negative 1..7, 2*window <= 64
+        const int r = launch_sg_fused_round(node, negemb, walks, walk_off, n_walks, reduced_windows, seeds, base_seed, table,
+                                            table_len, mu, inv_cov, pi, K, window, negative, lr, lambda1, lambda2,
+                                            is_node_embedding, atomic, n_rows, top1_comm, top1_weight, st);
+        if (r != COMEMB_E_UNSUPPORTED) return r;
+    }
+    // round-1 fast path: size 128, NEG in {3,4,5}, separate context table, window <= 12, pi one-hot (or lambda2 == 0)
     if (size == 128 && !is_node_embedding && negemb != node && 2 * window <= VMAX && negative >= 3 && negative <= 5 &&
         (comemb_opts().variant != COMEMB_VARIANT_GENERIC || top1)) {
         int32_t *comm = nullptr;

@@ -273,8 +273,11 @@ int launch_o3_batch(float *node, int64_t n_rows, int size, const uint32_t *rows,
     int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     size_t smem = (size_t)O3_WARPS * size * sizeof(float);
     const int variant = comemb_opts().variant;
-    if (!pi && size == 128 && variant != COMEMB_VARIANT_GENERIC && variant != COMEMB_VARIANT_ROUND1) {
-        // top-1 form at the headline size: grouped GEMM on the tensor cores (o3_gemm.cu)
+    if (!pi && size == 128 && (variant == COMEMB_VARIANT_TENSOR || (variant == COMEMB_VARIANT_DEFAULT && n_sel >= 1024))) {
+        // top-1 form at the headline size: grouped GEMM on the tensor cores (o3_gemm.cu).  Small selections stay on the
+        // CUDA-core kernels below: they are latency-bound either way, and the double-accumulated dot is the more accurate
+        // one on ill-conditioned covariances (karate: 34 points in 128 dimensions give |inv_cov| ~ 1e5, where any two
+        // fp32 summation orders -- the reference's BLAS included -- differ by more than 1e-5 of the row).
         const int r = launch_o3_gemm(node, rows, n_sel, mu, inv_cov_t, comm, weight, K, scale, lr, iters, st);
         if (r != COMEMB_E_UNSUPPORTED) return r;
     }

@@ -165,20 +165,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmPara
         for (int it = 0; it < P.iters; it++) {
             // ---- B operand: diff rows, hi/lo split, swizzled K-major ----------------------------------------------------
             const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
-            for (int r = warp; r < cnt; r += WARPS) {
-                const uint32_t row = __ldg(P.srows + start + r);
-                const float4 x = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row * D + 4 * lane));
-                const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
-                const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y), umma::tf32_round(df.z),
-                                              umma::tf32_round(df.w));
-                const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
-                                              umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
-                const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
-                *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
-                *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
-                if (it == 0 && lane == 0) {
-                    row_s[r] = row;
-                    wgt_s[r] = __ldg(P.weight + row);
+            constexpr int RPW = (TN + WARPS - 1) / WARPS;  // rows per warp: all gathers in flight before the first use
+            uint32_t rowv[RPW];
+            float4 xv[RPW];
+#pragma unroll
+            for (int q = 0; q < RPW; q++) {
+                const int r = warp + q * WARPS;
+                rowv[q] = r < cnt ? __ldg(P.srows + start + r) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < RPW; q++) {
+                const int r = warp + q * WARPS;
+                if (r < cnt) xv[q] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)rowv[q] * D + 4 * lane));
+            }
+#pragma unroll
+            for (int q = 0; q < RPW; q++) {
+                const int r = warp + q * WARPS;
+                if (r < cnt) {
+                    const float4 x = xv[q];
+                    const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+                    const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y), umma::tf32_round(df.z),
+                                                  umma::tf32_round(df.w));
+                    const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
+                                                  umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
+                    const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
+                    *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
+                    *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
+                    if (it == 0 && lane == 0) {
+                        row_s[r] = rowv[q];
+                        wgt_s[r] = __ldg(P.weight + rowv[q]);
+                    }
                 }
             }
             umma::fence_proxy_async_smem();
@@ -202,21 +218,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmPara
             // ---- epilogue: thread = output coordinate a of TMEM lane quarter (warp % 4), 16 rows at a time ----------------
             const int a = 32 * (warp & 3) + lane;
             for (int ch = warp >> 2; ch * 16 < n16; ch += WARPS / 4) {
-                float v[16];
+                float v[16], xo[16];
                 umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ch * 16), v);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {  // the 16 old values first: independent loads, one latency
+                    const int n = ch * 16 + q;
+                    xo[q] = n < cnt ? __ldcg(P.node + (int64_t)row_s[n] * D + a) : 0.f;
+                }
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const int n = ch * 16 + q;
                     if (n < cnt) {
-                        float *xp = P.node + (int64_t)row_s[n] * D + a;
                         float g = __fmul_rn(__fmul_rn(wgt_s[n], v[q]), P.scale);  // :71, :76
                         g = fminf(fmaxf(g, -5.f), 5.f);                           // :77
-                        *xp = __ldcg(xp) - __fmul_rn(g, P.lr);
+                        P.node[(int64_t)row_s[n] * D + a] = xo[q] - __fmul_rn(g, P.lr);
                     }
                 }
             }
             umma::tc_fence_before();
-            __threadfence_block();
+            __threadfence();
             __syncthreads();  // accumulator and B images are free again; the updated rows are visible to the CTA
         }
     }
@@ -237,7 +257,7 @@ int launch_umma_prep_a(const float *P, char *out, int K, cudaStream_t st) {
 // top-1 form at size 128; returns COMEMB_E_UNSUPPORTED when the shape does not fit (the caller falls back)
 int launch_o3_gemm(float *node, const uint32_t *rows, int64_t n_sel, const float *mu, const float *inv_cov_t,
                    const int32_t *comm, const float *weight, int K, float scale, float lr, int iters, cudaStream_t st) {
-    constexpr int TN = 64, WARPS = 8;
+    constexpr int TN = 64, WARPS = 16;
     using L = O3GemmSmem<TN>;
     if (n_sel <= 0 || iters <= 0) return 0;
     if (n_sel >= (1LL << 31) || K > (1 << 20)) return COMEMB_E_UNSUPPORTED;
