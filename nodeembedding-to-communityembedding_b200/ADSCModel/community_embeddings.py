@@ -62,13 +62,26 @@ class Community2Vec(object):
         return abs(total) * (beta / model.k)
 
     def train(self, nodes, model, beta, chunksize=150, iter=1):
+        """`nodes` may list a node more than once.  The reference adds the node's (frozen) gradient once per CHUNK the
+        node occurs in -- `grad_input[node_index] += batch_grad_input` is a buffered fancy-index add, so repeats inside
+        one chunk of `chunksize` collapse, repeats in different chunks accumulate (:64-73) -- and applies the sum once.
+        The gradient is linear in pi, so the same result is the single-occurrence update with the node's
+        responsibilities scaled by that multiplicity; every row is updated by exactly one warp/tile."""
         import torch
         dev = model.node_embedding.device
         rows = _rows_of(model, nodes)
+        pi = model.pi.contiguous()
+        if rows.size and np.unique(rows).size != rows.size:
+            chunk = np.arange(rows.size, dtype=np.int64) // int(chunksize)
+            pairs = np.unique(rows.astype(np.int64) * (int(chunk[-1]) + 1) + chunk)
+            rows, mult = np.unique((pairs // (int(chunk[-1]) + 1)).astype(np.uint32), return_counts=True)
+            if (mult != 1).any():
+                pi = pi.clone()
+                sel_m = torch.from_numpy(rows.astype(np.int64)).to(dev)
+                pi[sel_m] *= torch.from_numpy(mult.astype(np.float32)).to(dev)[:, None]
         rows_d = torch.from_numpy(rows.view(np.int32)).to(dev)
         with torch.cuda.device(dev):
             inv_t = K.transpose_blocks(model.inv_covariance_mat.contiguous())
-            pi = model.pi.contiguous()
             # Rows whose pi has at most one non-zero entry (sklearn's predict_proba is one-hot in fp32 on separated
             # data) take the top-1 form: same arithmetic, but rows are grouped by community on the device and share
             # the inv_cov reads.  The others keep the dense form.

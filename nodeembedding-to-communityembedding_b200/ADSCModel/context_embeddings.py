@@ -3,8 +3,10 @@
 
 Same constructor and `train(model, paths, total_nodes, alpha, node_count, chunksize)`.  The whole walk corpus is one
 kernel launch (see node_embeddings.py for the workers -> mode rule).  `paths` may be an iterable of node-id
-sequences (the reference's convention) or a `(walks, lens)` pair of CUDA tensors of CSR/row tokens straight from the
-device walker, in which case nothing touches the host.
+sequences (the reference's convention) or CUDA tensors straight from the device walker, in which case nothing touches
+the host: `(walks, lens, G)` = CSR-row tokens of graph G, remapped on the device to table rows (Model.walks_to_rows:
+CSR rows follow the first appearance of an id in the edge file, table rows follow the sorted ids), or `(walks, lens)` =
+tokens that already ARE table rows.
 """
 import logging as log
 import time
@@ -45,8 +47,10 @@ class Context2Vec(object):
         start = time.time()
         dev = model.node_embedding.device
         mode = self._mode()
-        if isinstance(paths, tuple) and len(paths) == 2 and hasattr(paths[0], "is_cuda"):
-            walks2d, lens = paths  # device walker output: [n, L] padded with TOKEN_NONE
+        if isinstance(paths, tuple) and len(paths) in (2, 3) and hasattr(paths[0], "is_cuda"):
+            walks2d, lens = paths[0], paths[1]  # device walker output: [n, L] padded with TOKEN_NONE
+            if len(paths) == 3:  # CSR rows of that graph -> table rows
+                walks2d = model.walks_to_rows(paths[2], walks2d)
             n_walks, L = walks2d.shape
             if model.down_sampling:  # prepare_sentences' frequent-node filter, on the device
                 from .. import _lib

@@ -73,6 +73,33 @@ class Model(object):
             self._id_index = (ids, rows, probs)
         return self._id_index
 
+    def graph_row_lut(self, G):
+        """Device LUT from the CSR rows of graph `G` (first-appearance order of the ids, utils/graph_utils.Graph) to the
+        rows of this model's tables (rank of the node id, model.py:60-65), -1 for nodes outside the vocabulary; None when
+        the two orders coincide (ids sorted and all in the vocabulary -- every synthetic generator), so that the common
+        case costs nothing.  The device walker emits CSR rows; the tables are indexed by vocabulary rows."""
+        import torch
+        ids, rows, _ = self.id_index()
+        gid = np.asarray(G.ids, np.int64)
+        pos = np.searchsorted(ids, gid)
+        pos[pos >= ids.size] = 0
+        ok = ids[pos] == gid
+        lut = np.where(ok, rows[pos], -1).astype(np.int32)
+        if ok.all() and np.array_equal(lut, np.arange(gid.size, dtype=np.int32)):
+            return None
+        return torch.from_numpy(lut).to(self.device)
+
+    def walks_to_rows(self, G, walks):
+        """CSR-row walk tokens of `G` (TOKEN_NONE padding kept) -> table-row tokens; out-of-vocabulary nodes become
+        TOKEN_NONE, which the kernels skip like the reference skips `None` (pyx:485-486)."""
+        import torch
+        lut = self.graph_row_lut(G)
+        if lut is None:
+            return walks
+        ext = torch.cat([lut, torch.full((1,), -1, dtype=torch.int32, device=lut.device)])
+        idx = torch.where(walks < 0, torch.full_like(walks, lut.numel()), walks).long()
+        return ext[idx]
+
     # ---- tables (model.py:83-92) -----------------------------------------------------------------------------------------
     def reset_weights(self):
         import torch

@@ -30,6 +30,9 @@
 // Any pi: top-1 form (community + weight per row: plain result stores) or dense rows (one request per non-zero
 // responsibility, results accumulated with red.add and cleared by the consumer); negative 1..7; window span <= 64;
 // is_node_embedding 0/1; window shrinking; atomic or plain scatter.
+#include <cstdio>
+#include <cstdlib>
+
 #include "comemb_common.cuh"
 #include "umma.cuh"
 
@@ -71,6 +74,7 @@ struct RoundParams {
     unsigned *bar;         // grid barrier: {arrivals, generation}
     unsigned long long *walk_cursor;
     int *err;
+    long long *stats;      // optional (debug): block 0 accumulates clock64 cycles per phase {bar1, gemm, bar2, sgns, stage, rounds}
     int vslots;            // result slots per warp (>= 2*window)
     int64_t active_warps;  // Hogwild concurrency cap (warps that take walks)
 };
@@ -294,8 +298,15 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
     bool a_pending = false;
     bool ok = true;
 
+    long long t_prev = clock64(), acc[6] = {0, 0, 0, 0, 0, 0};
+    auto lap = [&](int slot) {
+        const long long now = clock64();
+        acc[slot] += now - t_prev;
+        t_prev = now;
+    };
     while (true) {
         if (!(ok = grid_sync(P.bar, gridDim.x, P.err, s_flag))) break;
+        lap(0);
         const int *cnt_g = P.count + par * (K + 1);
         if (__ldcg(cnt_g + K) == 0) break;  // no warp staged a centre: every walk is finished
         // ---- [gemm] -----------------------------------------------------------------------------------------------------------
@@ -427,7 +438,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
                 __syncthreads();  // accumulator, B images and the tile's slot list are free again
             }
         }
+        __syncthreads();
+        lap(1);
         if (!(ok = grid_sync(P.bar, gridDim.x, P.err, s_flag))) break;
+        lap(2);
         // ---- [sgns] of the staged centre, then stage the next one -------------------------------------------------------------
         if (have) {
             float *pos_ptr = ctx_l + (int64_t)wi * D;
@@ -590,8 +604,13 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
             }
         }
         par ^= 1;
+        lap(3);
         stage_next(par);
+        lap(4);
+        acc[5]++;
     }
+    if (P.stats && blockIdx.x == 0 && (threadIdx.x & 31) == 0)  // per warp of block 0: bar1 gemm bar2 sgns stage rounds
+        for (int q = 0; q < 6; q++) P.stats[warp * 6 + q] = acc[q];
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(taddr, TMEM_COLS);
 }
@@ -717,6 +736,13 @@ int launch_sg_fused_round(float *node, float *negemb, const uint32_t *walks, con
     P.err = reinterpret_cast<int *>(scratch + o_ctl + 32);
     P.count = reinterpret_cast<int *>(scratch + o_ctl + 256);
     P.vslots = vslots; P.active_warps = warps;
+    static const bool want_stats = getenv("COMEMB_ROUND_STATS") != nullptr;
+    long long *d_stats = nullptr;
+    if (want_stats) {
+        cudaMalloc(&d_stats, NW * 6 * sizeof(long long));
+        cudaMemset(d_stats, 0, NW * 6 * sizeof(long long));
+    }
+    P.stats = d_stats;
     switch (negative) {
         case 1: e = launch_round_t<1>(P, atomic, grid, st); break;
         case 2: e = launch_round_t<2>(P, atomic, grid, st); break;
@@ -725,6 +751,16 @@ int launch_sg_fused_round(float *node, float *negemb, const uint32_t *walks, con
         case 5: e = launch_round_t<5>(P, atomic, grid, st); break;
         case 6: e = launch_round_t<6>(P, atomic, grid, st); break;
         default: e = launch_round_t<7>(P, atomic, grid, st); break;
+    }
+    if (want_stats) {
+        long long h[NW * 6];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(d_stats);
+        for (int w = 0; w < NW; w += 5)
+            fprintf(stderr, "[round stats] block 0 warp %2d: rounds %lld  cycles/round: bar1 %lld gemm %lld bar2 %lld sgns %lld stage %lld\n",
+                    w, h[w * 6 + 5], h[w * 6 + 0] / (h[w * 6 + 5] + 1), h[w * 6 + 1] / (h[w * 6 + 5] + 1),
+                    h[w * 6 + 2] / (h[w * 6 + 5] + 1), h[w * 6 + 3] / (h[w * 6 + 5] + 1), h[w * 6 + 4] / (h[w * 6 + 5] + 1));
     }
     cudaFreeAsync(scratch, st);
     return (int)e;

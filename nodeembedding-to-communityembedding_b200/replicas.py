@@ -56,6 +56,7 @@ class ReplicaTrainer(object):
                                                mode=gu.MODE_HOGWILD, return_device=True,
                                                first_walk=pass_index * n + first, n_out=count)
         off = torch.arange(count + 1, dtype=torch.int64, device=walks.device) * path_length
+        walks = self.model.walks_to_rows(G, walks)  # CSR rows -> table rows (identity for sorted dense ids)
         K.o2_batch(self.model.node_embedding, self.model.context_embedding, walks.reshape(-1), off, None, self.lr,
                    self.negative, self.window, self.model.table, mode=K.MODE_HOGWILD, flags=self.flags,
                    base_seed=seed * 1000003 + pass_index * 8191 + self.rank)

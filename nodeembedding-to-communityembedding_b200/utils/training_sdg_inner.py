@@ -33,7 +33,7 @@ def __getattr__(name):  # FAST_VERSION = init() at first use (the reference runs
 
 
 # ---- host <-> device plumbing ----------------------------------------------------------------------------------------
-_const_cache = {}  # (host address, nbytes, dtype) -> device tensor, for read-only inputs (the negative table)
+_const_cache = {}  # (host address, nbytes, dtype, crc32 of the contents) -> device copy of a negative table
 
 
 def clear_cache():
@@ -71,8 +71,11 @@ class _Borrowed(object):
             self.host[...] = self.dev.cpu().numpy()
 
 
-def _const_dev(arr, dtype):
-    """Read-only input (table, centroids ...) as a device tensor; numpy inputs are cached by buffer identity."""
+def _const_dev(arr, dtype, cache=False):
+    """Read-only input as a device tensor.  numpy inputs are uploaded on every call; only the negative table
+    (`cache=True`: tens to hundreds of MB, rebuilt rarely) is kept on the device between calls, keyed by its address,
+    size AND a checksum of its full contents, so an in-place rebuild can never be served from a stale copy.  The small
+    GMM inputs (centroid / inv_cov / pi, refit in place between calls) are never cached."""
     torch = _torch()
     if arr is None:
         return None
@@ -84,15 +87,15 @@ def _const_dev(arr, dtype):
             raise ComembError("expected %s, got %s" % (want, arr.dtype))
         return arr.contiguous()
     a = np.ascontiguousarray(arr, dtype=dtype)
-    # identity alone is not enough (a freed buffer's address is reused): add a strided content fingerprint
-    flat = a.reshape(-1)
-    step = max(1, flat.size // 4096)
-    key = (a.ctypes.data, a.nbytes, a.dtype.str, hash(flat[::step].tobytes()), hash(flat[-64:].tobytes()))
+    view = a.view(np.int32) if a.dtype == np.uint32 else a
+    if not cache:
+        return torch.from_numpy(view).cuda()
+    import zlib
+    key = (a.ctypes.data, a.nbytes, a.dtype.str, zlib.crc32(memoryview(a).cast("B")))
     hit = _const_cache.get(key)
     if hit is None:
-        if len(_const_cache) > 8:
+        if len(_const_cache) > 4:
             _const_cache.clear()
-        view = a.view(np.int32) if a.dtype == np.uint32 else a
         hit = torch.from_numpy(view).cuda()
         _const_cache[key] = hit
     return hit
@@ -196,7 +199,7 @@ class HostO2Runner(object):
 
     def __init__(self, n_rows, size, max_tokens, max_walks, table):
         torch = _torch()
-        self.table = _const_dev(table, np.uint32)
+        self.table = _const_dev(table, np.uint32, cache=True)
         pin = dict(pin_memory=True)
         self.h_node = torch.empty((n_rows, size), dtype=torch.float32, **pin)
         self.h_ctx = torch.empty((n_rows, size), dtype=torch.float32, **pin)
@@ -359,7 +362,7 @@ def train_o1(py_node_embedding, py_edge, py_lr, py_negative, py_table, py_size=N
         # the reference reads uninitialised indexes[] here (pyx:444); we refuse
         raise ComembError("train_o1 needs an edge of two in-vocabulary nodes")
     edges = torch.from_numpy(idx[:2].view(np.int32).copy()).cuda()
-    o1_batch(node.dev, edges, _dev(seed, np.uint64), py_lr, py_negative, _const_dev(py_table, np.uint32),
+    o1_batch(node.dev, edges, _dev(seed, np.uint64), py_lr, py_negative, _const_dev(py_table, np.uint32, cache=True),
              mode=MODE_ORDERED, flags=flags)
     node.writeback()
     return result
@@ -380,7 +383,7 @@ def train_o2(py_node_embedding, py_context_embedding, py_path, py_lr, py_negativ
         walks = torch.from_numpy(idx.view(np.int32)).cuda()
         off = torch.tensor([0, len(idx)], dtype=torch.int64, device="cuda")
         o2_batch(node.dev, ctx.dev, walks, off, _dev(seed, np.uint64), py_lr, py_negative, py_window,
-                 _const_dev(py_table, np.uint32), alpha=py_alpha, mode=MODE_ORDERED, flags=flags)
+                 _const_dev(py_table, np.uint32, cache=True), alpha=py_alpha, mode=MODE_ORDERED, flags=flags)
     node.writeback()
     ctx.writeback()
     return result
@@ -408,7 +411,7 @@ def train_sg(py_node_embedding, py_negative_embedding, py_path, py_alpha, py_neg
         walks = torch.from_numpy(idx.view(np.int32)).cuda()
         off = torch.tensor([0, len(idx)], dtype=torch.int64, device="cuda")
         sg_batch(node.dev, neg.dev, walks, off, _dev(rw, np.int32), _dev(seed, np.uint64), py_alpha, py_negative,
-                 py_window, _const_dev(py_table, np.uint32), _const_dev(py_centroid, np.float32),
+                 py_window, _const_dev(py_table, np.uint32, cache=True), _const_dev(py_centroid, np.float32),
                  _const_dev(py_inv_covariance_mat, np.float32), _const_dev(py_pi, np.float32), py_lambda1, py_lambda2,
                  py_is_node_embedding, mode=MODE_ORDERED, flags=flags)
     node.writeback()

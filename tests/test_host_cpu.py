@@ -272,3 +272,33 @@ def test_community2vec_row_lookup_matches_the_dict_loop():
         assert _rows_of(m, iter([1, 9])).tolist() == [3, 2]
         with pytest.raises(KeyError):
             _rows_of(m, [9, 2])
+
+
+def test_graph_rows_are_remapped_to_table_rows():
+    """CSR rows follow the first appearance of an id in the edge file, table rows follow the sorted ids
+    (model.py:60-65): for the reference's karate file the two differ, and walks from the device walker must be mapped
+    before they index the tables (round-1 advisor finding)."""
+    import torch
+    from comemb_b200.ADSCModel.model import Model
+    from comemb_b200.utils import graph_utils as gu
+    from comemb_b200.utils.embedding import Vocab
+    G = gu.load_adjacencylist(os.path.join(ROOT, "tests", "golden", "karate.adjlist"))
+    assert not np.array_equal(G.ids, np.sort(G.ids))  # first-appearance order is not sorted for this file
+    m = Model.__new__(Model)
+    m.device, m._id_index, m.vocab = "cpu", None, {}
+    for row, node in enumerate(sorted(int(i) for i in G.ids if i != 12)):  # node 12 left out of the vocabulary
+        m.vocab[node] = Vocab(count=1, index=row, sample_probability=1.0)
+    lut = m.graph_row_lut(G)
+    assert lut is not None and lut.shape[0] == len(G)
+    for csr_row, node in enumerate(G.ids):
+        assert int(lut[csr_row]) == (m.vocab[int(node)].index if int(node) in m.vocab else -1)
+    walks = torch.tensor([[0, 5, 33, -1], [int(np.flatnonzero(G.ids == 12)[0]), 1, -1, -1]], dtype=torch.int32)
+    rows = m.walks_to_rows(G, walks)
+    assert rows[0, 3] == -1 and rows[1, 0] == -1 and rows[1, 2] == -1  # padding kept, OOV node dropped
+    assert int(rows[0, 1]) == m.vocab[int(G.ids[5])].index
+    # sorted dense ids (every synthetic generator): no LUT, tokens pass through untouched
+    G2 = gu.from_edge_array_fast(np.array([[1, 2], [2, 3], [3, 1]]), 3)
+    m2 = Model.__new__(Model)
+    m2.device, m2._id_index = "cpu", None
+    m2.vocab = {i: Vocab(count=2, index=i - 1, sample_probability=1.0) for i in (1, 2, 3)}
+    assert m2.graph_row_lut(G2) is None and m2.walks_to_rows(G2, walks) is walks
