@@ -53,6 +53,7 @@ int comemb_abi_version(void);
  * launches the calling thread makes afterwards (NULL restores the defaults), so two threads -- or one thread per GPU -- never
  * see each other's settings.  No entry point keeps process-global mutable state. */
 #define COMEMB_VARIANT_DEFAULT 0       /* the fastest kernel for the shape */
+#define COMEMB_VARIANT_ROUNDSYNC 3     /* fused pass: the round-synchronous tcgen05 kernel even where the asynchronous one applies */
 #define COMEMB_VARIANT_TENSOR 4        /* tensor-core kernels even below the size where they become the default (tests) */
 #define COMEMB_VARIANT_L2_HINTS 5      /* size-128 Hogwild o2: L2 eviction-priority hints (experiment) */
 #define COMEMB_VARIANT_ROUND1 6        /* round-1 kernels: fp64-pipe top-1 o3, per-warp mma.sync fused pass */

@@ -58,8 +58,8 @@ class ComembOpts(ctypes.Structure):
                 ("max_warps", _i64)]
 
 
-(VARIANT_DEFAULT, VARIANT_TENSOR, VARIANT_L2_HINTS, VARIANT_ROUND1, VARIANT_ORDERED_PIPE, VARIANT_ORDERED_PLAIN,
- VARIANT_GENERIC) = (0, 4, 5, 6, 7, 8, 9)
+(VARIANT_DEFAULT, VARIANT_ROUNDSYNC, VARIANT_TENSOR, VARIANT_L2_HINTS, VARIANT_ROUND1, VARIANT_ORDERED_PIPE,
+ VARIANT_ORDERED_PLAIN, VARIANT_GENERIC) = (0, 3, 4, 5, 6, 7, 8, 9)
 
 
 class ComembError(RuntimeError):

@@ -1,0 +1,559 @@
+// fused_async.cu -- the fast HOGWILD form of the legacy fused pass (stale train_sg: per window pair the o3 community
+// gradient of x_j, the SGNS pair update and the combined write; utils/training_sdg_inner.c:1597-1905, 2520-2715,
+// 2988-3740) at size 128 with pi in top-1 form: ONE persistent cooperative kernel, warp-specialised, no grid barrier.
+//
+// The o3 term is a 128x128 mat-vec per pair against the inverse covariance of x_j's community; a window holds ~4.5
+// communities, so a warp alone can batch only ~4 rows per community (round 1 streamed 64 KB of inv_cov from L2 per such
+// group).  Here the batching is done ACROSS the ~3000 walks in flight, asynchronously:
+//
+//   one CTA per SM; 20 WALKER warps + 4 SERVICE warps per CTA.
+//   walker warp (owns a walk, one centre at a time, exactly the o2 kernel's order):
+//     [stage]  lists the rows of its next window; every row whose o3 term can be taken from the row's value at the start
+//              of the centre (all but a node that repeats inside the window) becomes a request {row, result slot} appended
+//              to the queue of (its community, replica) -- a ring in global memory, tail reserved with one warp-aggregated
+//              atomicAdd per community, entries published with single 8-byte stores;
+//     [wait]   until its completion counter shows that all requests of the centre were served;
+//     [sgns]   the centre's pairs (fused_sgns.cuh): SGNS on the o2 size-128 code path + the combined write with the o3
+//              term from its result slots; repeated nodes get the term in-warp from the current value, so a walk sees the
+//              reference's sequential semantics exactly.
+//   service warps of a CTA own the queues q with q % gridDim == blockIdx (community c has n_rep replicas so that every SM
+//   serves): they pop up to 64 requests, keep inv_cov_c resident in shared memory as the tcgen05 A operand (hi/lo TF32
+//   images, fetched by the TMA engine with cp.async.bulk only on a community switch), gather the rows, form x - mu_c,
+//   split hi/lo into the swizzled B operand, one thread issues 48 tcgen05.mma (3xTF32: fp32-level accuracy, accumulator in
+//   TMEM), read the accumulator back with tcgen05.ld, write w*Y to the result slots and bump the requesters' counters.
+//
+// Nothing waits on a barrier that another CTA must reach: walkers wait only for results, service warps only for
+// published entries, so the SGNS half runs at the o2 kernel's pace while the tensor half hides behind it.
+#include <cstdio>
+#include <cstdlib>
+
+#include "comemb_common.cuh"
+#include "fused_sgns.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using fused::INFO_INWARP;
+constexpr int D = 128;
+constexpr int TN = 64;                      // requests per GEMM tile (tcgen05 N)
+constexpr int VMAX = 64;                    // window rows per centre (2*window <= 64)
+constexpr int A_IMG_BYTES = 2 * D * D * 4;  // hi + lo operand images of one community
+constexpr int NSVC = 4;                     // service warps (warps 0..3 of the CTA: one per TMEM lane quarter)
+constexpr int MAXQ = 64;                    // queues one CTA can own
+constexpr unsigned long long EMPTY = ~0ULL;
+constexpr long long WAIT_TIMEOUT = 8000000000LL;  // ~4 s of SM clocks: a protocol bug must end the kernel, not hang the GPU
+
+struct AsyncParams {
+    float *node, *ctx;
+    const uint32_t *walks;
+    const int64_t *walk_off;
+    int64_t n_walks;
+    const int32_t *rw;
+    const uint64_t *seeds;
+    uint64_t base_seed;
+    const uint32_t *table;
+    TableMod mod;
+    const float *mu, *inv_cov;
+    const char *a_img;
+    const int32_t *comm;
+    const float *weight;
+    int K, window, is_node;
+    float lr, lambda1, lambda2;
+    const float *glut;
+    // scratch
+    float *ybuf;                // [total warps * vslots][128]
+    unsigned long long *ring;   // [Q][cap] request entries: row | slot << 32, EMPTY when free
+    unsigned *tail;             // [Q * 8]: reserved entries per queue (one 32-byte sector each)
+    unsigned *done;             // [total warps]: served requests per walker warp (monotonic)
+    int *live;                  // walker warps that still have work
+    unsigned long long *walk_cursor;
+    int *err;
+    long long *stats;
+    int64_t cap;                // ring capacity (power of two >= all requests that can be outstanding)
+    int n_rep, Q, vslots;
+    int64_t active_warps;
+};
+
+template <int NW>
+struct AsyncSmem {
+    static constexpr int A_HI = 0, A_LO = D * D * 4, B_HI = 2 * D * D * 4, B_LO = B_HI + TN * D * 4;
+    static constexpr int MU = B_LO + TN * D * 4;   // float[128]
+    static constexpr int ROW = MU + D * 4;         // uint32[TN] rows of the tile
+    static constexpr int SLOT = ROW + TN * 4;      // uint32[TN] result slots
+    static constexpr int WGT = SLOT + TN * 4;      // float[TN]
+    static constexpr int LUT = WGT + TN * 4;       // float[1000]
+    static constexpr int HEAD = LUT + 4096;        // uint32[MAXQ] consumed entries per owned queue
+    static constexpr int WTOK = HEAD + MAXQ * 4;   // per walker warp: uint32 tok[VMAX]
+    static constexpr int WINF = WTOK + NW * VMAX * 4;
+    static constexpr int WX = WINF + NW * VMAX * 4;  // per walker warp: float xs[128]
+    static constexpr int BAR = (WX + NW * D * 4 + 15) & ~15;
+    static constexpr int TOTAL = BAR + 64;
+};
+
+__device__ __forceinline__ void svc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NSVC * 32) : "memory"); }
+__device__ __forceinline__ unsigned ld_vol(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+
+template <bool ATOMIC, int NEG, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams P) {
+    using L = AsyncSmem<NW>;
+    constexpr LcgJump<NEG> J{};
+    constexpr uint32_t TMEM_COLS = 64;
+    extern __shared__ char smem_raw[];
+    char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *lut = reinterpret_cast<float *>(smem + L::LUT);
+    uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 2);
+    int *sel = reinterpret_cast<int *>(bar_a + 3);  // sel[0] = owned-queue index, sel[1] = requests to take (-1: exit)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    if (warp == 0) umma::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x == 0) {
+        umma::mbar_init(bar_a, 1);
+        umma::mbar_init(bar_mma, 1);
+        umma::fence_mbar_init();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t taddr = *tmem_slot;
+    const int K = P.K;
+
+    if (warp < NSVC) {
+        // =============================== SERVICE WARPS ===================================================================
+        float *mu_s = reinterpret_cast<float *>(smem + L::MU);
+        uint32_t *row_s = reinterpret_cast<uint32_t *>(smem + L::ROW);
+        uint32_t *slot_s = reinterpret_cast<uint32_t *>(smem + L::SLOT);
+        float *wgt_s = reinterpret_cast<float *>(smem + L::WGT);
+        uint32_t *head = reinterpret_cast<uint32_t *>(smem + L::HEAD);
+        const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
+        const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
+        const int tid = threadIdx.x;  // 0..127
+        int nq = 0;                   // queues owned by this CTA: q = blockIdx.x + i * gridDim.x
+        for (int q = blockIdx.x; q < P.Q; q += gridDim.x) nq++;
+        for (int i = tid; i < nq; i += NSVC * 32) head[i] = 0;
+        svc_barrier();
+        int cur_c = -1, rr = 0;
+        uint32_t par_a = 0, par_m = 0;
+        bool a_pending = false;
+        long long tiles = 0, rows_served = 0, idle_polls = 0;
+        while (true) {
+            if (tid == 0) {
+                int best = -1;
+                unsigned bestn = 0;
+                for (int pass = 0; pass < 2 && best < 0; pass++) {
+                    const int live = pass == 0 ? 1 : *reinterpret_cast<volatile int *>(P.live);
+                    for (int i = 0; i < nq; i++) {
+                        const int idx = (rr + i) % nq;
+                        const int q = blockIdx.x + idx * gridDim.x;
+                        const unsigned pend = ld_vol(P.tail + q * 8) - head[idx];
+                        // stay on the resident community while it has work; otherwise the fullest queue
+                        const unsigned score = pend + ((pend && q / P.n_rep == cur_c) ? 0x40000000u : 0u);
+                        if (score > bestn) {
+                            bestn = score;
+                            best = idx;
+                        }
+                    }
+                    if (best >= 0 || pass == 1) {
+                        if (best >= 0) {
+                            const unsigned pend = bestn & 0x3FFFFFFFu;
+                            sel[0] = best;
+                            sel[1] = (int)(pend < (unsigned)TN ? pend : (unsigned)TN);
+                            rr = best;
+                        } else {
+                            sel[1] = live == 0 ? -1 : 0;  // the queues were re-read AFTER live was seen at zero
+                        }
+                        break;
+                    }
+                    if (*reinterpret_cast<volatile int *>(P.live) != 0) {  // nothing pending, walkers still running
+                        sel[1] = 0;
+                        break;
+                    }
+                }
+            }
+            svc_barrier();
+            const int n = sel[1], qi = sel[0];
+            if (n < 0) break;
+            if (n == 0) {
+                idle_polls++;
+                __nanosleep(200);
+                svc_barrier();
+                continue;
+            }
+            const int q = blockIdx.x + qi * gridDim.x;
+            const int c = q / P.n_rep;
+            const int n16 = (n + 15) & ~15;
+            const uint32_t base = head[qi];
+            if (tid < n) {  // pop: wait for the entry to be published, take it, mark the ring position free
+                volatile unsigned long long *p = P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1));
+                unsigned long long e = *p;
+                const long long t0 = clock64();
+                while (e == EMPTY) {
+                    if (clock64() - t0 > WAIT_TIMEOUT) {
+                        *P.err = 2;
+                        e = 0;
+                        break;
+                    }
+                    e = *p;
+                }
+                *p = EMPTY;
+                const uint32_t row = (uint32_t)e;
+                row_s[tid] = row;
+                slot_s[tid] = (uint32_t)(e >> 32);
+                wgt_s[tid] = __ldg(P.weight + row);
+            }
+            __threadfence();  // acquire: the requester's row updates precede its published entry
+            if (c != cur_c) {  // every MMA that read the resident A has completed (bar_mma is waited on per tile)
+                if (tid == 0) {
+                    umma::mbar_expect_tx(bar_a, A_IMG_BYTES);
+                    const char *src = P.a_img + (int64_t)c * A_IMG_BYTES;
+#pragma unroll
+                    for (int qq = 0; qq < 8; qq++) umma::bulk_g2s(smem + L::A_HI + qq * 16384, src + qq * 16384, 16384, bar_a);
+                }
+                if (warp == 1)
+                    *reinterpret_cast<float4 *>(mu_s + 4 * lane) =
+                        __ldg(reinterpret_cast<const float4 *>(P.mu + (int64_t)c * D + 4 * lane));
+                a_pending = true;
+                cur_c = c;
+            }
+            svc_barrier();
+            if (tid == 0) head[qi] = base + (uint32_t)n;
+            // B operand: 16 rows per warp, gathers in flight 8 at a time
+            const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                float4 xv[8];
+#pragma unroll
+                for (int qq = 0; qq < 8; qq++) {
+                    const int r = warp + NSVC * (half * 8 + qq);
+                    if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_s[r] * D + 4 * lane));
+                }
+#pragma unroll
+                for (int qq = 0; qq < 8; qq++) {
+                    const int r = warp + NSVC * (half * 8 + qq);
+                    if (r < n) {
+                        const float4 x = xv[qq];
+                        const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+                        const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y),
+                                                      umma::tf32_round(df.z), umma::tf32_round(df.w));
+                        const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
+                                                      umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
+                        const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
+                        *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
+                        *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
+                    }
+                }
+            }
+            umma::fence_proxy_async_smem();
+            svc_barrier();
+            if (warp == 0) {
+                if (a_pending) {
+                    umma::mbar_wait(bar_a, par_a);
+                    par_a ^= 1;
+                }
+                umma::tc_fence_after();
+                if (lane == 0) {
+                    umma::issue_3xtf32(taddr, a_hi, a_lo, b_hi, b_lo, TN, n16);
+                    umma::mma_commit(bar_mma);
+                }
+                __syncwarp();
+            }
+            a_pending = false;
+            umma::mbar_wait(bar_mma, par_m);
+            par_m ^= 1;
+            umma::tc_fence_after();
+            // epilogue: service warp w reads TMEM lanes 32w..32w+31 (output coordinates), 16 requests at a time
+            const int a = 32 * warp + lane;
+            for (int ch = 0; ch * 16 < n16; ch++) {
+                float v[16];
+                umma::tmem_ld16(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)(ch * 16), v);
+#pragma unroll
+                for (int qq = 0; qq < 16; qq++) {
+                    const int nn = ch * 16 + qq;
+                    if (nn < n) P.ybuf[(int64_t)slot_s[nn] * D + a] = __fmul_rn(wgt_s[nn], v[qq]);
+                }
+            }
+            umma::tc_fence_before();
+            __threadfence();
+            svc_barrier();
+            if (tid < n) {  // release: the results precede the counter the requester polls
+                __threadfence();
+                atomicAdd(P.done + slot_s[tid] / (uint32_t)P.vslots, 1u);
+            }
+            tiles++;
+            rows_served += n;
+            svc_barrier();  // row_s / slot_s / wgt_s are free for the next tile
+        }
+        if (P.stats && tid == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 0), (unsigned long long)tiles);
+            atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 1), (unsigned long long)rows_served);
+            atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 2), (unsigned long long)idle_polls);
+        }
+    } else {
+        // =============================== WALKER WARPS ====================================================================
+        constexpr int NWALK = NW - NSVC;
+        const int ww = warp - NSVC;
+        uint32_t *tokS = reinterpret_cast<uint32_t *>(smem + L::WTOK) + ww * VMAX;
+        int32_t *infS = reinterpret_cast<int32_t *>(smem + L::WINF) + ww * VMAX;
+        float *xs = reinterpret_cast<float *>(smem + L::WX) + ww * D;
+        const int W = P.window;
+        const int64_t gwarp = (int64_t)blockIdx.x * NWALK + ww;
+        const bool walker = gwarp < P.active_warps;
+        const int64_t slot0 = gwarp * P.vslots;
+        const int rep = (int)(gwarp % P.n_rep);
+        fused::SgnsArgs SA;
+        SA.node = P.node; SA.ctx = P.ctx; SA.table = P.table; SA.mod = P.mod; SA.mu = P.mu; SA.inv_cov = P.inv_cov;
+        SA.weight = P.weight; SA.pi = nullptr; SA.ybuf = P.ybuf; SA.K = K; SA.dense = false; SA.o3_on = true;
+        SA.is_node = P.is_node != 0; SA.lr = P.lr; SA.lambda1 = P.lambda1; SA.nl2 = -P.lambda2;            // c:3132
+        SA.clipv = __double2float_rn(__dmul_rn((double)P.lr, 0.1));                                         // c:2556
+        uint64_t myA = 1, myC = 0;
+#pragma unroll
+        for (int k = 0; k < NEG; k++)
+            if (lane == k) {
+                myA = J.A[k];
+                myC = J.C[k];
+            }
+        const uint32_t *path = nullptr;
+        const int32_t *rwp = nullptr;
+        int len = 0, ci = -1, V = 0;
+        uint32_t wi = 0, tnext = 0, expected = 0;
+        uint64_t rnd = 0;
+        bool exhausted = !walker;
+        long long t_wait = 0, t_sgns = 0, t_stage = 0, centres = 0;
+        while (!exhausted) {
+            const long long t0 = clock64();
+            // ---- [stage] the next centre with a non-empty window ---------------------------------------------------------
+            bool have = false;
+            int n_req = 0;
+            while (!exhausted) {
+                ci++;
+                if (ci >= len) {  // next walk
+                    unsigned long long w = 0;
+                    if (lane == 0) w = atomicAdd(P.walk_cursor, 1ULL);
+                    w = __shfl_sync(FULL, w, 0);
+                    if ((int64_t)w >= P.n_walks) {
+                        exhausted = true;
+                        break;
+                    }
+                    const int64_t o0 = __ldg(P.walk_off + w), o1 = __ldg(P.walk_off + w + 1);
+                    path = P.walks + o0;
+                    rwp = P.rw ? P.rw + o0 : nullptr;
+                    len = (int)min((int64_t)MAX_SENTENCE_LEN, o1 - o0);
+                    rnd = P.seeds ? P.seeds[w] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+                    tnext = (lane < NEG) ? __ldg(P.table + table_slot((myA * rnd + myC) & LCG_MASK, P.mod)) : 0u;
+                    rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+                    ci = -1;
+                    continue;
+                }
+                wi = __ldg(path + ci);
+                if (wi == COMEMB_TOKEN_NONE) continue;
+                const int r = rwp ? rwp[ci] : 0;
+                const int ja = max(0, ci - W + r), jb = min(len, ci + W + 1 - r);
+                int v = 0;
+                __syncwarp();
+                for (int base = ja; base < jb; base += 32) {  // window rows in position order
+                    const int jl = base + lane;
+                    uint32_t tk = COMEMB_TOKEN_NONE;
+                    if (jl < jb && jl != ci) tk = __ldg(path + jl);
+                    const bool valid = tk != COMEMB_TOKEN_NONE;
+                    const unsigned vm = __ballot_sync(FULL, valid);
+                    if (valid) tokS[v + __popc(vm & ((1u << lane) - 1u))] = tk;
+                    v += __popc(vm);
+                }
+                V = v;
+                if (V == 0) continue;
+                __syncwarp();
+                __threadfence();  // release (cumulative over the warp): the previous centre's row updates precede the entries
+                for (int base = 0; base < V; base += 32) {
+                    const int vv = base + lane;
+                    const bool mine = vv < V;
+                    const uint32_t tk = mine ? tokS[vv] : 0u;
+                    bool dup = false;  // an earlier window position holds the same node: o3 from the current value, in-warp
+                    for (int u = 0; u < vv && mine; u++) dup = dup || (tokS[u] == tk);
+                    int c = -1;
+                    if (mine) {
+                        c = __ldg(P.comm + tk);
+                        if (c >= K || (c >= 0 && __ldg(P.weight + tk) == 0.f)) c = -1;
+                    }
+                    const int key = (mine && c >= 0 && !dup) ? c : -1 - lane;  // unique negative keys for non-requests
+                    const unsigned peers = __match_any_sync(FULL, key);
+                    if (key >= 0) {
+                        const int leader = __ffs(peers) - 1;
+                        const int q = c * P.n_rep + rep;
+                        unsigned basep = 0;
+                        if (lane == leader) basep = atomicAdd(P.tail + q * 8, (unsigned)__popc(peers));
+                        basep = __shfl_sync(peers, basep, leader);
+                        const unsigned at = (basep + (unsigned)__popc(peers & ((1u << lane) - 1u))) & (unsigned)(P.cap - 1);
+                        *reinterpret_cast<volatile unsigned long long *>(P.ring + (int64_t)q * P.cap + at) =
+                            (unsigned long long)tk | ((unsigned long long)(uint32_t)(slot0 + vv) << 32);
+                    }
+                    n_req += __popc(__ballot_sync(FULL, key >= 0));
+                    if (mine) infS[vv] = c < 0 ? -1 : (dup ? (c | INFO_INWARP) : c);
+                }
+                __syncwarp();
+                have = true;
+                break;
+            }
+            if (!have) break;
+            const long long t1 = clock64();
+            // ---- [wait] for the centre's results ----------------------------------------------------------------------------
+            expected += (unsigned)n_req;
+            bool ok = true;
+            if (n_req > 0) {
+                if (lane == 0) {
+                    while ((int)(ld_vol(P.done + gwarp) - expected) < 0) {
+                        __nanosleep(64);
+                        if (clock64() - t1 > WAIT_TIMEOUT) {
+                            *P.err = 3;
+                            ok = false;
+                            break;
+                        }
+                    }
+                    __threadfence();  // acquire
+                }
+                ok = __shfl_sync(FULL, ok, 0);
+                __syncwarp();
+            }
+            if (!ok) break;
+            const long long t2 = clock64();
+            // ---- [sgns] -----------------------------------------------------------------------------------------------------
+            fused::sgns_centre<ATOMIC, NEG>(SA, wi, V, tokS, infS, xs, lut, slot0, rnd, tnext, myA, myC, lane);
+            const long long t3 = clock64();
+            t_stage += t1 - t0;
+            t_wait += t2 - t1;
+            t_sgns += t3 - t2;
+            centres++;
+        }
+        __syncwarp();
+        if (walker && lane == 0) {
+            __threadfence();
+            atomicSub(P.live, 1);
+            if (P.stats && centres) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 3), (unsigned long long)t_stage);
+                atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 4), (unsigned long long)t_wait);
+                atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 5), (unsigned long long)t_sgns);
+                atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 6), (unsigned long long)centres);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(taddr, TMEM_COLS);
+}
+
+template <int NEG>
+cudaError_t launch_async_t(const AsyncParams &P, bool atomic, int grid, cudaStream_t st) {
+    constexpr int NW = 24;
+    const int smem = AsyncSmem<NW>::TOTAL + 1024;
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        void *args[] = {const_cast<AsyncParams *>(&P)};
+        return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(NW * 32), args, (size_t)smem, st);
+    };
+    return atomic ? go(sg_async_kernel<true, NEG, NW>) : go(sg_async_kernel<false, NEG, NW>);
+}
+
+}  // namespace
+
+int launch_umma_prep_a(const float *P, char *out, int K, cudaStream_t st);
+
+// pi in top-1 form (comm / weight per table row), lambda2 != 0.  Returns COMEMB_E_UNSUPPORTED when the shape does not fit
+// (the caller falls back to the round-synchronous or the generic kernel).
+int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
+                          const int32_t *reduced_windows, const uint64_t *seeds, uint64_t base_seed, const uint32_t *table,
+                          uint64_t table_len, const float *mu, const float *inv_cov, int K, int window, int negative,
+                          float lr, float lambda1, float lambda2, int is_node_embedding, bool atomic,
+                          const int32_t *comm, const float *weight, cudaStream_t st) {
+    constexpr int NW = 24, NWALK = NW - NSVC;
+    if (negative < 1 || negative > 7 || window < 1 || 2 * window > VMAX || lambda2 == 0.f) return COMEMB_E_UNSUPPORTED;
+    if (K < 1 || !mu || !inv_cov || !comm || !weight) return COMEMB_E_UNSUPPORTED;
+    if (!is_node_embedding && negemb == node) return COMEMB_E_UNSUPPORTED;
+    if (n_walks <= 0) return 0;
+    int dev = 0, sms = 148, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return COMEMB_E_UNSUPPORTED;
+    int64_t warps = (int64_t)sms * NWALK;
+    if (comemb_opts().max_warps > 0 && comemb_opts().max_warps < warps) warps = comemb_opts().max_warps;
+    if (n_walks < warps) warps = n_walks;
+    const int grid = (int)((warps + NWALK - 1) / NWALK);
+    int n_rep = grid / K;  // replicas per community so that (almost) every SM's service warps own a queue
+    n_rep = n_rep < 1 ? 1 : (n_rep > 4 ? 4 : n_rep);
+    const int Q = K * n_rep;
+    if ((Q + grid - 1) / grid > MAXQ) return COMEMB_E_UNSUPPORTED;
+    const int64_t total_warps = (int64_t)grid * NWALK;
+    const int vslots = 2 * window;
+    // a walker has at most vslots requests in flight, so total_warps * vslots bounds the entries of one queue that are
+    // reserved and not yet popped; twice that keeps a ring position's reuse far away from the pop that freed it
+    int64_t cap = 64;
+    while (cap < 2 * total_warps * vslots) cap <<= 1;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        const size_t at = off;
+        off = (off + bytes + 1023) & ~(size_t)1023;
+        return at;
+    };
+    const size_t sz_ctl = 256 + (size_t)Q * 32 + (size_t)total_warps * 4;
+    const size_t o_ctl = carve(sz_ctl), o_y = carve((size_t)total_warps * vslots * D * 4);
+    const size_t o_ring = carve((size_t)Q * cap * 8), o_img = carve((size_t)K * A_IMG_BYTES);
+    if (off > ((size_t)24 << 30)) return COMEMB_E_UNSUPPORTED;
+    char *scratch = nullptr;
+    CUDA_TRY(cudaMallocAsync(&scratch, off, st));
+    auto fail = [&](cudaError_t e) {
+        cudaFreeAsync(scratch, st);
+        return (int)e;
+    };
+    cudaError_t e = cudaMemsetAsync(scratch + o_ctl, 0, sz_ctl, st);
+    if (e != cudaSuccess) return fail(e);
+    if ((e = cudaMemsetAsync(scratch + o_ring, 0xFF, (size_t)Q * cap * 8, st)) != cudaSuccess) return fail(e);
+    const int h_live = (int)warps;
+    if ((e = cudaMemcpyAsync(scratch + o_ctl + 48, &h_live, 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
+    const int r = launch_umma_prep_a(inv_cov, scratch + o_img, K, st);
+    if (r) return fail((cudaError_t)r);
+    AsyncParams P;
+    P.node = node; P.ctx = negemb; P.walks = walks; P.walk_off = walk_off; P.n_walks = n_walks; P.rw = reduced_windows;
+    P.seeds = seeds; P.base_seed = base_seed; P.table = table; P.mod = make_table_mod(table_len);
+    P.mu = mu; P.inv_cov = inv_cov; P.a_img = scratch + o_img; P.comm = comm; P.weight = weight;
+    P.K = K; P.window = window; P.is_node = is_node_embedding; P.lr = lr; P.lambda1 = lambda1; P.lambda2 = lambda2;
+    P.glut = comemb_lut_device();
+    P.ybuf = reinterpret_cast<float *>(scratch + o_y);
+    P.ring = reinterpret_cast<unsigned long long *>(scratch + o_ring);
+    P.walk_cursor = reinterpret_cast<unsigned long long *>(scratch + o_ctl + 16);
+    P.err = reinterpret_cast<int *>(scratch + o_ctl + 32);
+    P.live = reinterpret_cast<int *>(scratch + o_ctl + 48);
+    P.tail = reinterpret_cast<unsigned *>(scratch + o_ctl + 256);
+    P.done = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 32);
+    P.cap = cap; P.n_rep = n_rep; P.Q = Q; P.vslots = vslots; P.active_warps = warps;
+    static const bool want_stats = getenv("COMEMB_ROUND_STATS") != nullptr;
+    long long *d_stats = nullptr;
+    if (want_stats) {
+        cudaMalloc(&d_stats, 8 * sizeof(long long));
+        cudaMemset(d_stats, 0, 8 * sizeof(long long));
+    }
+    P.stats = d_stats;
+    switch (negative) {
+        case 1: e = launch_async_t<1>(P, atomic, grid, st); break;
+        case 2: e = launch_async_t<2>(P, atomic, grid, st); break;
+        case 3: e = launch_async_t<3>(P, atomic, grid, st); break;
+        case 4: e = launch_async_t<4>(P, atomic, grid, st); break;
+        case 5: e = launch_async_t<5>(P, atomic, grid, st); break;
+        case 6: e = launch_async_t<6>(P, atomic, grid, st); break;
+        default: e = launch_async_t<7>(P, atomic, grid, st); break;
+    }
+    if (want_stats) {
+        long long h[8];
+        int h_err = 0;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&h_err, P.err, 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_stats);
+        fprintf(stderr,
+                "[async stats] grid %d n_rep %d Q %d err %d: tiles %lld rows %lld (%.1f rows/tile) idle polls %lld | per centre "
+                "cycles: stage %lld wait %lld sgns %lld (centres %lld)\n",
+                grid, n_rep, Q, h_err, h[0], h[1], h[0] ? (double)h[1] / h[0] : 0.0, h[2], h[3] / (h[6] + 1),
+                h[4] / (h[6] + 1), h[5] / (h[6] + 1), h[6]);
+    }
+    cudaFreeAsync(scratch, st);
+    return (int)e;
+}

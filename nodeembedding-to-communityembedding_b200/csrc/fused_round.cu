@@ -34,6 +34,7 @@
 #include <cstdlib>
 
 #include "comemb_common.cuh"
+#include "fused_sgns.cuh"
 #include "umma.cuh"
 
 int launch_umma_prep_a(const float *P, char *out, int K, cudaStream_t st);
@@ -94,7 +95,7 @@ struct RoundSmem {
     static constexpr int TOTAL = BAR + 64;
 };
 
-constexpr int INFO_INWARP = 1 << 30;
+using fused::INFO_INWARP;
 
 // ---- grid-wide barrier (all CTAs are co-resident: cooperative launch) ------------------------------------------------------------
 // Returns false when the barrier timed out (another CTA died): the caller leaves its loops and tears down.
@@ -126,8 +127,6 @@ __device__ __forceinline__ bool grid_sync(unsigned *bar, unsigned n_ctas, int *e
     __syncthreads();
     return *s_flag != 0;
 }
-
-__device__ __forceinline__ float clipf(float v, float c) { return fminf(fmaxf(v, -c), c); }
 
 template <bool ATOMIC, int NEG, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams P) {
@@ -183,6 +182,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
     const int64_t gwarp = (int64_t)blockIdx.x * NW + warp;
     const bool walker = gwarp < P.active_warps;
     const int64_t slot0 = gwarp * P.vslots;
+    fused::SgnsArgs SA;
+    SA.node = P.node; SA.ctx = P.ctx; SA.table = P.table; SA.mod = P.mod; SA.mu = P.mu; SA.inv_cov = P.inv_cov;
+    SA.weight = P.weight; SA.pi = P.pi; SA.ybuf = P.ybuf; SA.K = K; SA.dense = dense; SA.o3_on = o3_on;
+    SA.is_node = is_node; SA.lr = lr; SA.lambda1 = lambda1; SA.nl2 = nl2; SA.clipv = clipv;
 
     // ---- per-warp walk state (registers; the kernel is persistent) ---------------------------------------------------------
     const uint32_t *path = nullptr;
@@ -443,166 +446,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
         if (!(ok = grid_sync(P.bar, gridDim.x, P.err, s_flag))) break;
         lap(2);
         // ---- [sgns] of the staged centre, then stage the next one -------------------------------------------------------------
-        if (have) {
-            float *pos_ptr = ctx_l + (int64_t)wi * D;
-            float4 cpos = __ldcg(reinterpret_cast<const float4 *>(pos_ptr));
-            float4 dpos = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int v = 0; v < V; v++) {
-                const uint32_t wj = tokS[v];
-                float *row1_ptr = node_l + (int64_t)wj * D;
-                const float4 r1 = __ldcg(reinterpret_cast<const float4 *>(row1_ptr));
-                // ---- o3 term of x_j -----------------------------------------------------------------------------------------
-                float4 o3 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (o3_on) {
-                    const int inf = infS[v];
-                    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-                    bool any = false;
-                    if (!(inf & INFO_INWARP) && (dense || inf >= 0)) {  // taken from the tensor-core result
-                        float *yp = P.ybuf + (slot0 + v) * D + 4 * lane;
-                        y = __ldcg(reinterpret_cast<const float4 *>(yp));
-                        if (dense) __stcg(reinterpret_cast<float4 *>(yp), make_float4(0.f, 0.f, 0.f, 0.f));
-                        any = true;
-                    } else if (inf >= 0 && (inf & INFO_INWARP)) {  // repeated node: from the current value, in-warp
-                        const int k0 = dense ? 0 : (inf & ~INFO_INWARP), k1 = dense ? K : k0 + 1;
-                        for (int k = k0; k < k1; k++) {
-                            const float p = dense ? __ldg(P.pi + (int64_t)wj * K + k) : __ldg(P.weight + wj);
-                            if (p == 0.f) continue;
-                            const float4 mk = __ldg(reinterpret_cast<const float4 *>(P.mu + (int64_t)k * D + 4 * lane));
-                            __syncwarp();
-                            *reinterpret_cast<float4 *>(xs + 4 * lane) =
-                                make_float4(r1.x - mk.x, r1.y - mk.y, r1.z - mk.z, r1.w - mk.w);
-                            __syncwarp();
-                            const float4 *S = reinterpret_cast<const float4 *>(P.inv_cov + (int64_t)k * D * D) + lane;
-                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-                            for (int b = 0; b < D; b++) {  // column-major read: operand element (a,b) = S[b*128 + a]
-                                const float4 s = __ldg(S + b * 32);
-                                const float d = xs[b];
-                                t.x = fmaf(s.x, d, t.x); t.y = fmaf(s.y, d, t.y);
-                                t.z = fmaf(s.z, d, t.z); t.w = fmaf(s.w, d, t.w);
-                            }
-                            y.x = fmaf(p, t.x, y.x); y.y = fmaf(p, t.y, y.y);
-                            y.z = fmaf(p, t.z, y.z); y.w = fmaf(p, t.w, y.w);
-                            any = true;
-                        }
-                    }
-                    if (any)
-                        o3 = make_float4(clipf(__fmul_rn(nl2, y.x), clipv), clipf(__fmul_rn(nl2, y.y), clipv),
-                                         clipf(__fmul_rn(nl2, y.z), clipv), clipf(__fmul_rn(nl2, y.w), clipv));
-                }
-                // ---- SGNS pair (centre wi, row wj) ---------------------------------------------------------------------------
-                if (is_node) cpos = __ldcg(reinterpret_cast<const float4 *>(pos_ptr));  // the "context" table may be the node table
-                const uint32_t tmine = tnext;
-                tnext = (lane < NEG) ? __ldg(P.table + table_slot((myA * rnd + myC) & LCG_MASK, P.mod)) : 0u;
-                rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
-                uint32_t tt[NEG];
-#pragma unroll
-                for (int k = 0; k < NEG; k++) tt[k] = __shfl_sync(FULL, tmine, k);
-                bool anydup = false;
-#pragma unroll
-                for (int k = 1; k < NEG; k++)
-#pragma unroll
-                    for (int a = 0; a < k; a++) anydup = anydup || (tt[a] == tt[k]);
-                float4 work = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!anydup || is_node) {  // no context writes with is_node_embedding: equal samples cannot interact
-                    float4 c[NEG];
-#pragma unroll
-                    for (int k = 0; k < NEG; k++) c[k] = __ldcg(reinterpret_cast<const float4 *>(ctx_l + (int64_t)tt[k] * D));
-                    float p[8];
-                    p[0] = fmaf(r1.w, cpos.w, fmaf(r1.z, cpos.z, fmaf(r1.y, cpos.y, fmaf(r1.x, cpos.x, 0.f))));
-#pragma unroll
-                    for (int k = 0; k < 7; k++)
-                        p[k + 1] = k < NEG ? fmaf(r1.w, c[k < NEG ? k : 0].w,
-                                                  fmaf(r1.z, c[k < NEG ? k : 0].z,
-                                                       fmaf(r1.y, c[k < NEG ? k : 0].y,
-                                                            fmaf(r1.x, c[k < NEG ? k : 0].x, 0.f))))
-                                           : 0.f;
-                    const float fm = reduce8_transposed(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], lane);
-                    bool live = pi_slot == 0;
-#pragma unroll
-                    for (int k = 0; k < NEG; k++) live = live || (pi_slot == k + 1 && tt[k] != wi);
-                    float gm = 0.f;
-                    if (live && fm > -MAX_EXP_F && fm < MAX_EXP_F) gm = __fmul_rn(my_label - lut[lut_index(fm)], lr);  // c:1813
-                    {
-                        const float gg = __shfl_sync(FULL, gm, lane_of_p(0));
-                        const float gl = __fmul_rn(gg, lambda1);  // c:1822
-                        work.x = fmaf(gg, cpos.x, work.x); work.y = fmaf(gg, cpos.y, work.y);
-                        work.z = fmaf(gg, cpos.z, work.z); work.w = fmaf(gg, cpos.w, work.w);
-                        if (!is_node) {  // c:1840-1859
-                            if (ATOMIC) {
-                                dpos.x = fmaf(gl, r1.x, dpos.x); dpos.y = fmaf(gl, r1.y, dpos.y);
-                                dpos.z = fmaf(gl, r1.z, dpos.z); dpos.w = fmaf(gl, r1.w, dpos.w);
-                            }
-                            cpos.x = fmaf(gl, r1.x, cpos.x); cpos.y = fmaf(gl, r1.y, cpos.y);
-                            cpos.z = fmaf(gl, r1.z, cpos.z); cpos.w = fmaf(gl, r1.w, cpos.w);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < NEG; k++) {
-                        const float gg = __shfl_sync(FULL, gm, lane_of_p(k + 1));
-                        const float gl = __fmul_rn(gg, lambda1);
-                        work.x = fmaf(gg, c[k].x, work.x); work.y = fmaf(gg, c[k].y, work.y);
-                        work.z = fmaf(gg, c[k].z, work.z); work.w = fmaf(gg, c[k].w, work.w);
-                        if (gg != 0.f && !is_node) {
-                            float *cp = ctx_l + (int64_t)tt[k] * D;
-                            if (ATOMIC)
-                                red_add4(cp, make_float4(__fmul_rn(gl, r1.x), __fmul_rn(gl, r1.y), __fmul_rn(gl, r1.z),
-                                                         __fmul_rn(gl, r1.w)));
-                            else
-                                st4(cp, make_float4(fmaf(gl, r1.x, c[k].x), fmaf(gl, r1.y, c[k].y), fmaf(gl, r1.z, c[k].z),
-                                                    fmaf(gl, r1.w, c[k].w)));
-                        }
-                    }
-                } else {  // equal samples inside one pair: target by target, re-reading rows
-                    {
-                        const float f = warp_sum_xor(
-                            fmaf(r1.w, cpos.w, fmaf(r1.z, cpos.z, fmaf(r1.y, cpos.y, fmaf(r1.x, cpos.x, 0.f)))));
-                        if (f > -MAX_EXP_F && f < MAX_EXP_F) {
-                            const float gg = __fmul_rn(1.f - lut[lut_index(f)], lr), gl = __fmul_rn(gg, lambda1);
-                            work.x = fmaf(gg, cpos.x, work.x); work.y = fmaf(gg, cpos.y, work.y);
-                            work.z = fmaf(gg, cpos.z, work.z); work.w = fmaf(gg, cpos.w, work.w);
-                            if (ATOMIC) {
-                                dpos.x = fmaf(gl, r1.x, dpos.x); dpos.y = fmaf(gl, r1.y, dpos.y);
-                                dpos.z = fmaf(gl, r1.z, dpos.z); dpos.w = fmaf(gl, r1.w, dpos.w);
-                            }
-                            cpos.x = fmaf(gl, r1.x, cpos.x); cpos.y = fmaf(gl, r1.y, cpos.y);
-                            cpos.z = fmaf(gl, r1.z, cpos.z); cpos.w = fmaf(gl, r1.w, cpos.w);
-                        }
-                    }
-#pragma unroll 1
-                    for (int k = 0; k < NEG; k++) {
-                        const uint32_t tkk = __shfl_sync(FULL, tmine, k);
-                        if (tkk == wi) continue;
-                        float *cp = ctx_l + (int64_t)tkk * D;
-                        const float4 c = __ldcg(reinterpret_cast<const float4 *>(cp));
-                        const float f = warp_sum_xor(fmaf(r1.w, c.w, fmaf(r1.z, c.z, fmaf(r1.y, c.y, fmaf(r1.x, c.x, 0.f)))));
-                        if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;
-                        const float gg = __fmul_rn(0.f - lut[lut_index(f)], lr), gl = __fmul_rn(gg, lambda1);
-                        work.x = fmaf(gg, c.x, work.x); work.y = fmaf(gg, c.y, work.y);
-                        work.z = fmaf(gg, c.z, work.z); work.w = fmaf(gg, c.w, work.w);
-                        if (ATOMIC)
-                            red_add4(cp, make_float4(__fmul_rn(gl, r1.x), __fmul_rn(gl, r1.y), __fmul_rn(gl, r1.z),
-                                                     __fmul_rn(gl, r1.w)));
-                        else
-                            st4(cp, make_float4(fmaf(gl, r1.x, c.x), fmaf(gl, r1.y, c.y), fmaf(gl, r1.z, c.z),
-                                                fmaf(gl, r1.w, c.w)));
-                    }
-                }
-                // combined write: x_j = fma(lambda1, work, x_j) + work_o3   (c:1870, c:3668)
-                if (ATOMIC)
-                    red_add4(row1_ptr, make_float4(fmaf(lambda1, work.x, o3.x), fmaf(lambda1, work.y, o3.y),
-                                                   fmaf(lambda1, work.z, o3.z), fmaf(lambda1, work.w, o3.w)));
-                else
-                    st4(row1_ptr, make_float4(fmaf(lambda1, work.x, r1.x) + o3.x, fmaf(lambda1, work.y, r1.y) + o3.y,
-                                              fmaf(lambda1, work.z, r1.z) + o3.z, fmaf(lambda1, work.w, r1.w) + o3.w));
-            }
-            if (!is_node) {
-                if (ATOMIC)
-                    red_add4(pos_ptr, dpos);
-                else
-                    st4(pos_ptr, cpos);
-            }
-        }
+        if (have)
+            fused::sgns_centre<ATOMIC, NEG>(SA, wi, V, tokS, infS, xs, lut, slot0, rnd, tnext, myA, myC, lane);
         par ^= 1;
         lap(3);
         stage_next(par);
@@ -649,6 +494,13 @@ cudaError_t launch_round_t(const RoundParams &P, bool atomic, int grid, cudaStre
 }
 
 }  // namespace
+
+// dense pi -> top-1 form; *d_flag (zeroed by the caller) receives 1 when a row has several non-zero responsibilities
+int fused_pi_to_top1(const float *pi, int64_t n_rows, int K, int32_t *comm, float *weight, int *d_flag, cudaStream_t st) {
+    if (n_rows <= 0) return COMEMB_E_ARG;
+    pi_top1_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(pi, n_rows, K, comm, weight, d_flag);
+    return (int)cudaGetLastError();
+}
 
 // Returns COMEMB_E_UNSUPPORTED when the shape does not fit this kernel (the caller falls back to the generic one).
 int launch_sg_fused_round(float *node, float *negemb, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,

@@ -15,6 +15,10 @@
 #include "comemb_common.cuh"
 
 
+int fused_pi_to_top1(const float *, int64_t, int, int32_t *, float *, int *, cudaStream_t);
+int launch_sg_fused_async(float *, float *, const uint32_t *, const int64_t *, int64_t, const int32_t *, const uint64_t *,
+                          uint64_t, const uint32_t *, uint64_t, const float *, const float *, int, int, int, float, float,
+                          float, int, bool, const int32_t *, const float *, cudaStream_t);
 int launch_sg_fused_round(float *, float *, const uint32_t *, const int64_t *, int64_t, const int32_t *, const uint64_t *,
                           uint64_t, const uint32_t *, uint64_t, const float *, const float *, const float *, int, int, int,
                           float, float, float, int, bool, int64_t, const int32_t *, const float *, cudaStream_t);
@@ -609,8 +613,40 @@ int launch_sg_fused_hogwild(float *node, float *negemb, int size, const uint32_t
     P.glut = comemb_lut_device();
     const bool top1 = top1_comm != nullptr;  // the caller already holds pi in top-1 form (and no dense pi)
     const int variant = comemb_opts().variant;
-    if (size == 128 && (variant == COMEMB_VARIANT_DEFAULT || variant == COMEMB_VARIANT_TENSOR)) {
-        // the round-synchronous kernel with the o3 half on tcgen05 (fused_round.cu): any pi, negative 1..7, 2*window <= 64
+    if (size == 128 && (variant == COMEMB_VARIANT_DEFAULT || variant == COMEMB_VARIANT_TENSOR ||
+                        variant == COMEMB_VARIANT_ROUNDSYNC)) {
+        // tcgen05 kernels.  pi in top-1 form (given, or a dense pi that turns out one-hot): the asynchronous kernel
+        // (fused_async.cu); dense pi, lambda2 == 0 or COMEMB_VARIANT_ROUNDSYNC: the round-synchronous one (fused_round.cu).
+        if (lambda2 != 0.f && variant != COMEMB_VARIANT_ROUNDSYNC && (top1 || (pi && n_rows > 0))) {
+            const int32_t *c1 = top1_comm;
+            const float *w1 = top1_weight;
+            char *tmp = nullptr;
+            if (!top1) {
+                int h_flag = 1;
+                CUDA_TRY(cudaMallocAsync(&tmp, 16 + (size_t)n_rows * 8, st));
+                int32_t *cc = reinterpret_cast<int32_t *>(tmp + 16);
+                float *ww = reinterpret_cast<float *>(tmp + 16 + (size_t)n_rows * 4);
+                cudaError_t e = cudaMemsetAsync(tmp, 0, 16, st);
+                if (e == cudaSuccess) e = (cudaError_t)fused_pi_to_top1(pi, n_rows, K, cc, ww, reinterpret_cast<int *>(tmp), st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, tmp, 4, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) {
+                    cudaFreeAsync(tmp, st);
+                    return (int)e;
+                }
+                if (h_flag == 0) {
+                    c1 = cc;
+                    w1 = ww;
+                }
+            }
+            int r = COMEMB_E_UNSUPPORTED;
+            if (c1)
+                r = launch_sg_fused_async(node, negemb, walks, walk_off, n_walks, reduced_windows, seeds, base_seed, table,
+                                          table_len, mu, inv_cov, K, window, negative, lr, lambda1, lambda2,
+                                          is_node_embedding, atomic, c1, w1, st);
+            if (tmp) cudaFreeAsync(tmp, st);
+            if (r != COMEMB_E_UNSUPPORTED) return r;
+        }
         const int r = launch_sg_fused_round(node, negemb, walks, walk_off, n_walks, reduced_windows, seeds, base_seed, table,
                                             table_len, mu, inv_cov, pi, K, window, negative, lr, lambda1, lambda2,
                                             is_node_embedding, atomic, n_rows, top1_comm, top1_weight, st);

@@ -801,9 +801,12 @@ def _fast_sg_inputs(seed, N=400, K=6, nw=6, L=40, lam2=0.3, distinct=True):
     (0.3, False, False, 5, 5, False),   # repeated nodes inside a window: in-warp o3 from the current value
     (0.3, True, False, 1, 16, True),    # one negative, window 16 (span 33 > one lane pass), pi given in top-1 form
     (0.3, False, False, 7, 2, False), (0.5, True, False, 3, 10, True)])
-def test_sg_fused_fast_kernel_vs_oracle(K, lam2, shrink, distinct, neg, W, top1):
-    """The fast fused kernel (fused_round.cu: SGNS on the o2 size-128 code path, o3 as tcgen05 3xTF32 GEMM tiles batched
-    over the walks in flight), one walk per launch so that nothing races.  The kernel keeps the reference's sequential
+@pytest.mark.parametrize("kernel", ["async", "roundsync"])
+def test_sg_fused_fast_kernel_vs_oracle(K, lam2, shrink, distinct, neg, W, top1, kernel):
+    """The fast fused kernels -- fused_async.cu (default for one-hot / top-1 pi: walker warps + tcgen05 service warps,
+    request queues per community) and fused_round.cu (COMEMB_VARIANT_ROUNDSYNC; also the default for dense pi and
+    lambda2 == 0): SGNS on the o2 size-128 code path, o3 as tcgen05 3xTF32 GEMM tiles batched over the walks in
+    flight -- one walk per launch so that nothing races.  The kernel keeps the reference's sequential
     semantics inside a walk (a node that occupies two positions of a window gets its o3 term from its current value),
     so it equals the oracle up to the rounding of the o3 mat-vec.  lambda2 == 0: bit-exact.  lambda2 > 0: <= 1e-5
     relative (max |diff| <= 1e-5 * max |table|) -- round 1's TF32 kernel needed a statistical bound here.  A sigma-LUT
@@ -817,14 +820,17 @@ def test_sg_fused_fast_kernel_vs_oracle(K, lam2, shrink, distinct, neg, W, top1)
     dn, dc, dt = dev(node), dev(ctx), dev(table)
     dmu, dinv, dpi = dev(mu), dev(inv), dev(pi)
     comm, weight = K.pi_top1(dpi)
+    from comemb_b200 import _lib
+    variant = _lib.VARIANT_ROUNDSYNC if kernel == "roundsync" else _lib.VARIANT_DEFAULT
     for w, s in zip(walks, seeds):
         rw = rs.randint(0, W, len(w)).astype(np.int32) if shrink else None
         a = (dn, dc, dev(w), dev(np.array([0, len(w)], np.int64)), None if rw is None else dev(rw),
              dev(np.array([s], np.uint64)), lr, neg, W, dt, dmu, dinv)
-        if top1:
-            K.sg_batch_top1(*a, comm, weight, l1, lam2)
-        else:
-            K.sg_batch(*a, dpi, l1, lam2, 0, mode=K.MODE_HOGWILD)
+        with _lib.opts(variant=variant):
+            if top1:
+                K.sg_batch_top1(*a, comm, weight, l1, lam2)
+            else:
+                K.sg_batch(*a, dpi, l1, lam2, 0, mode=K.MODE_HOGWILD)
         O.train_sg(node, ctx, np.ascontiguousarray(w), rw, lr, neg, W, table, mu, inv, pi, l1, lam2, 0, int(s),
                    O.DOT_WARP)
     assert np.abs(node - node0).max() > 1e-3
@@ -835,9 +841,10 @@ def test_sg_fused_fast_kernel_vs_oracle(K, lam2, shrink, distinct, neg, W, top1)
             assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), np.abs(got - want).max()
 
 
-def test_sg_fused_fast_kernel_many_walks_in_flight_exact(K):
-    """The cross-walk batching itself, exactly: 600 walks over DISJOINT node sets run concurrently (25 CTAs, requests of
-    all walks pooled per community into multi-tile GEMM jobs) with lambda1 = 0, i.e. only the o3 term moves the rows and
+@pytest.mark.parametrize("kernel", ["async", "roundsync"])
+def test_sg_fused_fast_kernel_many_walks_in_flight_exact(K, kernel):
+    """The cross-walk batching itself, exactly: 600 walks over DISJOINT node sets run concurrently (25-30 CTAs, requests
+    of all walks pooled per community into multi-tile GEMM jobs) with lambda1 = 0, i.e. only the o3 term moves the rows and
     the context table is untouched -- no two warps touch the same row, so the result must equal the oracle's sequential
     run walk by walk: <= 1e-5 relative, for a dense pi with two non-zero responsibilities per row as well as top-1."""
     import torch
@@ -861,8 +868,10 @@ def test_sg_fused_fast_kernel_many_walks_in_flight_exact(K):
             pi[np.arange(N), rs.randint(0, Kc, size=N)] += rs.uniform(0.1, 0.4, size=N).astype(np.float32)
         pi[::17] = 0.0
         dn, dc = dev(node), dev(ctx)
-        K.sg_batch(dn, dc, dev(flat), dev(off), None, dev(seeds), 0.05, neg, W, dev(table), dev(mu), dev(inv), dev(pi),
-                   0.0, 0.4, 0, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC)
+        from comemb_b200 import _lib
+        with _lib.opts(variant=_lib.VARIANT_ROUNDSYNC if kernel == "roundsync" else _lib.VARIANT_DEFAULT):
+            K.sg_batch(dn, dc, dev(flat), dev(off), None, dev(seeds), 0.05, neg, W, dev(table), dev(mu), dev(inv),
+                       dev(pi), 0.0, 0.4, 0, mode=K.MODE_HOGWILD, flags=K.F_ATOMIC)
         want, wctx = node.copy(), ctx.copy()
         for w, sd in zip(walks, seeds):
             O.train_sg(want, wctx, w, None, 0.05, neg, W, table, mu, inv, pi, 0.0, 0.4, 0, int(sd), O.DOT_WARP)
