@@ -92,6 +92,25 @@ struct AsyncSmem {
 
 __device__ __forceinline__ void svc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NSVC * 32) : "memory"); }
 __device__ __forceinline__ unsigned ld_vol(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+// release / acquire at gpu scope: an entry (or a counter increment) published with release makes every write that
+// happened before it -- the publisher's own and, cumulatively, those it observed through a CTA/warp barrier -- visible to
+// the thread that acquires it
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <bool ATOMIC, int NEG, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams P) {
@@ -103,7 +122,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
     float *lut = reinterpret_cast<float *>(smem + L::LUT);
     uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 2);
-    int *sel = reinterpret_cast<int *>(bar_a + 3);  // sel[0] = owned-queue index, sel[1] = requests to take (-1: exit)
+    int *sel = reinterpret_cast<int *>(bar_a + 3);  // service scratch: 4 ints
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
@@ -133,76 +152,43 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         for (int q = blockIdx.x; q < P.Q; q += gridDim.x) nq++;
         for (int i = tid; i < nq; i += NSVC * 32) head[i] = 0;
         svc_barrier();
-        int cur_c = -1, rr = 0;
+        int cur_c = -1, qi = 0, zero_rot = 0, streak = 0;
         uint32_t par_a = 0, par_m = 0;
         bool a_pending = false;
         long long tiles = 0, rows_served = 0, idle_polls = 0;
+        int *pre = sel;  // pre[0], pre[1]: published-prefix lengths seen by warps 0 and 1; sel[2]: live walkers at probe time
         while (true) {
-            if (tid == 0) {
-                int best = -1;
-                unsigned bestn = 0;
-                for (int pass = 0; pass < 2 && best < 0; pass++) {
-                    const int live = pass == 0 ? 1 : *reinterpret_cast<volatile int *>(P.live);
-                    for (int i = 0; i < nq; i++) {
-                        const int idx = (rr + i) % nq;
-                        const int q = blockIdx.x + idx * gridDim.x;
-                        const unsigned pend = ld_vol(P.tail + q * 8) - head[idx];
-                        // stay on the resident community while it has work; otherwise the fullest queue
-                        const unsigned score = pend + ((pend && q / P.n_rep == cur_c) ? 0x40000000u : 0u);
-                        if (score > bestn) {
-                            bestn = score;
-                            best = idx;
-                        }
-                    }
-                    if (best >= 0 || pass == 1) {
-                        if (best >= 0) {
-                            const unsigned pend = bestn & 0x3FFFFFFFu;
-                            sel[0] = best;
-                            sel[1] = (int)(pend < (unsigned)TN ? pend : (unsigned)TN);
-                            rr = best;
-                        } else {
-                            sel[1] = live == 0 ? -1 : 0;  // the queues were re-read AFTER live was seen at zero
-                        }
-                        break;
-                    }
-                    if (*reinterpret_cast<volatile int *>(P.live) != 0) {  // nothing pending, walkers still running
-                        sel[1] = 0;
-                        break;
-                    }
-                }
+            // ---- probe the current queue: the next TN ring positions, published entries form a prefix ---------------------
+            const int q = nq ? blockIdx.x + qi * gridDim.x : 0;
+            const uint32_t base = nq ? head[qi] : 0u;
+            unsigned long long e = EMPTY;
+            if (tid == 0) sel[2] = *reinterpret_cast<volatile int *>(P.live);  // read BEFORE the entries
+            if (nq && tid < TN) e = ld_acquire_u64(P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1)));
+            if (warp < 2) {
+                const unsigned inval = __ballot_sync(FULL, e == EMPTY);
+                if (lane == 0) pre[warp] = inval ? __ffs(inval) - 1 : 32;
             }
             svc_barrier();
-            const int n = sel[1], qi = sel[0];
-            if (n < 0) break;
-            if (n == 0) {
+            const int n = pre[0] < 32 ? pre[0] : 32 + pre[1];
+            const int live = sel[2];
+            if (n == 0) {  // nothing published here: next owned queue; leave when every queue was seen empty with no walker left
                 idle_polls++;
-                __nanosleep(200);
-                svc_barrier();
+                zero_rot = live == 0 ? zero_rot + 1 : 0;
+                if (zero_rot > nq) break;
+                if (nq) qi = (qi + 1) % nq;
+                streak = 0;
+                __nanosleep(nq > 1 ? 20 : 100);
+                svc_barrier();  // pre/sel are rewritten by the next probe
                 continue;
             }
-            const int q = blockIdx.x + qi * gridDim.x;
+            zero_rot = 0;
             const int c = q / P.n_rep;
             const int n16 = (n + 15) & ~15;
-            const uint32_t base = head[qi];
-            if (tid < n) {  // pop: wait for the entry to be published, take it, mark the ring position free
-                volatile unsigned long long *p = P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1));
-                unsigned long long e = *p;
-                const long long t0 = clock64();
-                while (e == EMPTY) {
-                    if (clock64() - t0 > WAIT_TIMEOUT) {
-                        *P.err = 2;
-                        e = 0;
-                        break;
-                    }
-                    e = *p;
-                }
-                *p = EMPTY;
-                const uint32_t row = (uint32_t)e;
-                row_s[tid] = row;
+            if (tid < n) {  // take the entry, mark the ring position free
+                P.ring[(int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1))] = EMPTY;
+                row_s[tid] = (uint32_t)e;
                 slot_s[tid] = (uint32_t)(e >> 32);
-                wgt_s[tid] = __ldg(P.weight + row);
             }
-            __threadfence();  // acquire: the requester's row updates precede its published entry
             if (c != cur_c) {  // every MMA that read the resident A has completed (bar_mma is waited on per tile)
                 if (tid == 0) {
                     umma::mbar_expect_tx(bar_a, A_IMG_BYTES);
@@ -218,19 +204,18 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
             svc_barrier();
             if (tid == 0) head[qi] = base + (uint32_t)n;
-            // B operand: 16 rows per warp, gathers in flight 8 at a time
-            const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
+            // ---- B operand: 16 rows per warp, all gathers in flight before the first use ----------------------------------
+            {
+                const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
+                float4 xv[TN / NSVC];
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                float4 xv[8];
-#pragma unroll
-                for (int qq = 0; qq < 8; qq++) {
-                    const int r = warp + NSVC * (half * 8 + qq);
+                for (int qq = 0; qq < TN / NSVC; qq++) {
+                    const int r = warp + NSVC * qq;
                     if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_s[r] * D + 4 * lane));
                 }
 #pragma unroll
-                for (int qq = 0; qq < 8; qq++) {
-                    const int r = warp + NSVC * (half * 8 + qq);
+                for (int qq = 0; qq < TN / NSVC; qq++) {
+                    const int r = warp + NSVC * qq;
                     if (r < n) {
                         const float4 x = xv[qq];
                         const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
@@ -262,7 +247,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             umma::mbar_wait(bar_mma, par_m);
             par_m ^= 1;
             umma::tc_fence_after();
-            // epilogue: service warp w reads TMEM lanes 32w..32w+31 (output coordinates), 16 requests at a time
+            // ---- epilogue: service warp w reads TMEM lanes 32w..32w+31 (output coordinates), 16 requests at a time; the
+            // slot receives Y itself, the requester applies its responsibility ------------------------------------------------
             const int a = 32 * warp + lane;
             for (int ch = 0; ch * 16 < n16; ch++) {
                 float v[16];
@@ -270,19 +256,19 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
 #pragma unroll
                 for (int qq = 0; qq < 16; qq++) {
                     const int nn = ch * 16 + qq;
-                    if (nn < n) P.ybuf[(int64_t)slot_s[nn] * D + a] = __fmul_rn(wgt_s[nn], v[qq]);
+                    if (nn < n) P.ybuf[(int64_t)slot_s[nn] * D + a] = v[qq];
                 }
             }
             umma::tc_fence_before();
-            __threadfence();
-            svc_barrier();
-            if (tid < n) {  // release: the results precede the counter the requester polls
-                __threadfence();
-                atomicAdd(P.done + slot_s[tid] / (uint32_t)P.vslots, 1u);
-            }
+            svc_barrier();  // all four coordinate quarters of every result row are written ...
+            if (tid < n) red_release_add_u32(P.done + slot_s[tid] / (uint32_t)P.vslots, 1u);  // ... before the counter moves
             tiles++;
             rows_served += n;
-            svc_barrier();  // row_s / slot_s / wgt_s are free for the next tile
+            if (++streak >= 8 && nq > 1) {  // fairness among the queues of a CTA that owns several
+                streak = 0;
+                qi = (qi + 1) % nq;
+            }
+            svc_barrier();  // row_s / slot_s / pre are free for the next tile
         }
         if (P.stats && tid == 0) {
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 0), (unsigned long long)tiles);
@@ -362,8 +348,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 }
                 V = v;
                 if (V == 0) continue;
-                __syncwarp();
-                __threadfence();  // release (cumulative over the warp): the previous centre's row updates precede the entries
+                __syncwarp();  // every lane's row updates of the previous centre happen before the release stores below
                 for (int base = 0; base < V; base += 32) {
                     const int vv = base + lane;
                     const bool mine = vv < V;
@@ -384,8 +369,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                         if (lane == leader) basep = atomicAdd(P.tail + q * 8, (unsigned)__popc(peers));
                         basep = __shfl_sync(peers, basep, leader);
                         const unsigned at = (basep + (unsigned)__popc(peers & ((1u << lane) - 1u))) & (unsigned)(P.cap - 1);
-                        *reinterpret_cast<volatile unsigned long long *>(P.ring + (int64_t)q * P.cap + at) =
-                            (unsigned long long)tk | ((unsigned long long)(uint32_t)(slot0 + vv) << 32);
+                        st_release_u64(P.ring + (int64_t)q * P.cap + at,
+                                       (unsigned long long)tk | ((unsigned long long)(uint32_t)(slot0 + vv) << 32));
                     }
                     n_req += __popc(__ballot_sync(FULL, key >= 0));
                     if (mine) infS[vv] = c < 0 ? -1 : (dup ? (c | INFO_INWARP) : c);
@@ -401,15 +386,14 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             bool ok = true;
             if (n_req > 0) {
                 if (lane == 0) {
-                    while ((int)(ld_vol(P.done + gwarp) - expected) < 0) {
-                        __nanosleep(64);
+                    while ((int)(ld_acquire_u32(P.done + gwarp) - expected) < 0) {
+                        __nanosleep(32);
                         if (clock64() - t1 > WAIT_TIMEOUT) {
                             *P.err = 3;
                             ok = false;
                             break;
                         }
                     }
-                    __threadfence();  // acquire
                 }
                 ok = __shfl_sync(FULL, ok, 0);
                 __syncwarp();
@@ -478,7 +462,7 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     if (comemb_opts().max_warps > 0 && comemb_opts().max_warps < warps) warps = comemb_opts().max_warps;
     if (n_walks < warps) warps = n_walks;
     const int grid = (int)((warps + NWALK - 1) / NWALK);
-    int n_rep = grid / K;  // replicas per community so that (almost) every SM's service warps own a queue
+    int n_rep = (grid + K - 1) / K;  // replicas per community so that every SM's service warps own a queue
     n_rep = n_rep < 1 ? 1 : (n_rep > 4 ? 4 : n_rep);
     const int Q = K * n_rep;
     if ((Q + grid - 1) / grid > MAXQ) return COMEMB_E_UNSUPPORTED;

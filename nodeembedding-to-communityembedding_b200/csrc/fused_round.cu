@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
                         *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
                         if (lane == 0) {
                             slot_s[r] = slotv[q];
-                            wgt_s[r] = dense ? __ldcg(P.bw + lbase + r) : __ldg(P.weight + rowv[q]);
+                            if (dense) wgt_s[r] = __ldcg(P.bw + lbase + r);
                         }
                     }
                 }
@@ -429,11 +429,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
                         const int n = ch * 16 + q;
                         if (n < cnt) {
                             float *yp = P.ybuf + (int64_t)slot_s[n] * D + a;
-                            const float val = __fmul_rn(wgt_s[n], v[q]);
                             if (dense)
-                                atomicAdd(yp, val);  // one slot receives the terms of several communities
+                                atomicAdd(yp, __fmul_rn(wgt_s[n], v[q]));  // one slot receives the terms of several communities
                             else
-                                *yp = val;
+                                *yp = v[q];  // top-1 form: the consumer applies the responsibility
                         }
                     }
                 }

@@ -54,15 +54,18 @@ __device__ __forceinline__ void sgns_centre(const SgnsArgs &P, const uint32_t wi
         float *row1_ptr = node_l + (int64_t)wj * D;
         const float4 r1 = __ldcg(reinterpret_cast<const float4 *>(row1_ptr));
         // ---- o3 term of x_j -----------------------------------------------------------------------------------------
-        float4 o3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ysc = 1.f;
+        bool any = false;
         if (o3_on) {
             const int inf = infS[v];
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool any = false;
             if (!(inf & INFO_INWARP) && (dense || inf >= 0)) {  // taken from the tensor-core result
                 float *yp = P.ybuf + (slot0 + v) * D + 4 * lane;
                 y = __ldcg(reinterpret_cast<const float4 *>(yp));
-                if (dense) __stcg(reinterpret_cast<float4 *>(yp), make_float4(0.f, 0.f, 0.f, 0.f));
+                if (dense)
+                    __stcg(reinterpret_cast<float4 *>(yp), make_float4(0.f, 0.f, 0.f, 0.f));
+                else
+                    ysc = __ldg(P.weight + wj);  // top-1 form: the slot holds Y, the responsibility is applied here
                 any = true;
             } else if (inf >= 0 && (inf & INFO_INWARP)) {  // repeated node: from the current value, in-warp
                 const int k0 = dense ? 0 : (inf & ~INFO_INWARP), k1 = dense ? K : k0 + 1;
@@ -88,9 +91,6 @@ __device__ __forceinline__ void sgns_centre(const SgnsArgs &P, const uint32_t wi
                     any = true;
                 }
             }
-            if (any)
-                o3 = make_float4(clipf(__fmul_rn(nl2, y.x), clipv), clipf(__fmul_rn(nl2, y.y), clipv),
-                                 clipf(__fmul_rn(nl2, y.z), clipv), clipf(__fmul_rn(nl2, y.w), clipv));
         }
         // ---- SGNS pair (centre wi, row wj) ---------------------------------------------------------------------------
         if (is_node) cpos = __ldcg(reinterpret_cast<const float4 *>(pos_ptr));  // the "context" table may be the node table
@@ -190,7 +190,11 @@ __device__ __forceinline__ void sgns_centre(const SgnsArgs &P, const uint32_t wi
                                         fmaf(gl, r1.w, c.w)));
             }
         }
-        // combined write: x_j = fma(lambda1, work, x_j) + work_o3   (c:1870, c:3668)
+        // combined write: x_j = fma(lambda1, work, x_j) + work_o3   (c:1870, c:3668); work_o3 = clip(-lambda2 * w * Y)
+        float4 o3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (any)
+            o3 = make_float4(clipf(__fmul_rn(nl2, __fmul_rn(ysc, y.x)), clipv), clipf(__fmul_rn(nl2, __fmul_rn(ysc, y.y)), clipv),
+                             clipf(__fmul_rn(nl2, __fmul_rn(ysc, y.z)), clipv), clipf(__fmul_rn(nl2, __fmul_rn(ysc, y.w)), clipv));
         if (ATOMIC)
             red_add4(row1_ptr, make_float4(fmaf(lambda1, work.x, o3.x), fmaf(lambda1, work.y, o3.y),
                                            fmaf(lambda1, work.z, o3.z), fmaf(lambda1, work.w, o3.w)));
