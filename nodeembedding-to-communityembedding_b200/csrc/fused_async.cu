@@ -64,6 +64,7 @@ struct AsyncParams {
     float *ybuf;                // [total warps * vslots][128]
     unsigned long long *ring;   // [Q][cap] request entries: row | slot << 32, EMPTY when free
     unsigned *tail;             // [Q * 8]: reserved entries per queue (one 32-byte sector each)
+    unsigned *claim;            // [Q * 8]: entries claimed by service CTAs (claim <= tail)
     unsigned *done;             // [total warps]: served requests per walker warp (monotonic)
     int *live;                  // walker warps that still have work
     unsigned long long *walk_cursor;
@@ -148,44 +149,90 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
         const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
         const int tid = threadIdx.x;  // 0..127
-        int nq = 0;                   // queues owned by this CTA: q = blockIdx.x + i * gridDim.x
-        for (int q = blockIdx.x; q < P.Q; q += gridDim.x) nq++;
-        for (int i = tid; i < nq; i += NSVC * 32) head[i] = 0;
-        svc_barrier();
-        int cur_c = -1, qi = 0, zero_rot = 0, streak = 0;
+        int *pick = sel;  // pick[0..2] = {queue, first ring index, count} of the claimed tile; pick[3] = scratch
+        int *wbest = reinterpret_cast<int *>(head);  // per service warp: best key of the scan
+        int cur_c = -1, empty_scans = 0;
         uint32_t par_a = 0, par_m = 0;
         bool a_pending = false;
         long long tiles = 0, rows_served = 0, idle_polls = 0;
-        int *pre = sel;  // pre[0], pre[1]: published-prefix lengths seen by warps 0 and 1; sel[2]: live walkers at probe time
-        while (true) {
-            // ---- probe the current queue: the next TN ring positions, published entries form a prefix ---------------------
-            const int q = nq ? blockIdx.x + qi * gridDim.x : 0;
-            const uint32_t base = nq ? head[qi] : 0u;
-            unsigned long long e = EMPTY;
-            if (tid == 0) sel[2] = *reinterpret_cast<volatile int *>(P.live);  // read BEFORE the entries
-            if (nq && tid < TN) e = ld_acquire_u64(P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1)));
-            if (warp < 2) {
-                const unsigned inval = __ballot_sync(FULL, e == EMPTY);
-                if (lane == 0) pre[warp] = inval ? __ffs(inval) - 1 : 32;
+        long long ph[6] = {0, 0, 0, 0, 0, 0}, tp = clock64();
+        auto lap = [&](int k) {
+            const long long now = clock64();
+            ph[k] += now - tp;
+            tp = now;
+        };
+        // Pick the next tile: every service thread looks at the queues t, t+128, ...; the queue with the largest backlog
+        // wins, the resident community gets a bonus of 1.5 tiles (a switch costs a 128 KB operand fetch), and thread 0
+        // claims up to TN of its entries with one compare-and-swap (any CTA may serve any community: the load balances
+        // itself).  Result in pick[]; count 0 = nothing claimed, -1 = every walker has finished and all queues are empty.
+        auto choose_and_claim = [&]() {
+            const int live = tid == 0 ? *reinterpret_cast<volatile int *>(P.live) : 1;  // read BEFORE the queues
+            int key = 0;
+            for (int q = tid; q < P.Q; q += NSVC * 32) {
+                const int backlog = (int)(ld_vol(P.tail + q * 8) - ld_vol(P.claim + q * 8));
+                if (backlog > 0) {
+                    // + a CTA-specific tie-breaker so that the CTAs do not all rush to the same queue
+                    const int score = min(backlog, 1 << 19) + (q == cur_c ? (3 * TN) / 2 : 0) + ((q * 7 + (int)blockIdx.x * 13) & 31);
+                    key = max(key, (score << 11) | q);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
+            if (lane == 0) wbest[warp] = key;
+            svc_barrier();
+            if (tid == 0) {
+                int k = max(max(wbest[0], wbest[1]), max(wbest[2], wbest[3]));
+                int n = 0, q = 0;
+                unsigned h = 0;
+                if (k > 0) {
+                    q = k & 2047;
+                    for (int attempt = 0; attempt < 3 && n == 0; attempt++) {
+                        h = ld_vol(P.claim + q * 8);
+                        const int backlog = (int)(ld_vol(P.tail + q * 8) - h);
+                        if (backlog <= 0) break;
+                        const int want = min(backlog, TN);
+                        if (atomicCAS(P.claim + q * 8, h, h + (unsigned)want) == h) n = want;
+                    }
+                    empty_scans = 0;
+                } else if (live == 0) {
+                    if (++empty_scans >= 2) n = -1;
+                } else {
+                    empty_scans = 0;
+                }
+                pick[0] = q;
+                pick[1] = (int)h;
+                pick[2] = n;
             }
             svc_barrier();
-            const int n = pre[0] < 32 ? pre[0] : 32 + pre[1];
-            const int live = sel[2];
-            if (n == 0) {  // nothing published here: next owned queue; leave when every queue was seen empty with no walker left
+        };
+        choose_and_claim();
+        while (true) {
+            const int q = pick[0], n = pick[2];
+            const uint32_t base = (uint32_t)pick[1];
+            svc_barrier();  // everyone has read pick[] before it is rewritten
+            if (n < 0) break;
+            if (n == 0) {
                 idle_polls++;
-                zero_rot = live == 0 ? zero_rot + 1 : 0;
-                if (zero_rot > nq) break;
-                if (nq) qi = (qi + 1) % nq;
-                streak = 0;
-                __nanosleep(nq > 1 ? 20 : 100);
-                svc_barrier();  // pre/sel are rewritten by the next probe
+                __nanosleep(100);
+                choose_and_claim();
                 continue;
             }
-            zero_rot = 0;
-            const int c = q / P.n_rep;
+            lap(0);
+            const int c = q;
             const int n16 = (n + 15) & ~15;
-            if (tid < n) {  // take the entry, mark the ring position free
-                P.ring[(int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1))] = EMPTY;
+            if (tid < n) {  // the claimed entries are reserved, hence published within moments: take them, free the positions
+                unsigned long long *p = P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1));
+                unsigned long long e = ld_acquire_u64(p);
+                const long long t0 = clock64();
+                while (e == EMPTY) {
+                    if (clock64() - t0 > WAIT_TIMEOUT) {
+                        *P.err = 2;
+                        e = 0;
+                        break;
+                    }
+                    e = ld_acquire_u64(p);
+                }
+                *p = EMPTY;
                 row_s[tid] = (uint32_t)e;
                 slot_s[tid] = (uint32_t)(e >> 32);
             }
@@ -203,34 +250,38 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 cur_c = c;
             }
             svc_barrier();
-            if (tid == 0) head[qi] = base + (uint32_t)n;
-            // ---- B operand: 16 rows per warp, all gathers in flight before the first use ----------------------------------
+            lap(1);
+            // ---- B operand: 16 rows per warp, gathers in flight 8 at a time ---------------------------------------------------
             {
                 const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
-                float4 xv[TN / NSVC];
 #pragma unroll
-                for (int qq = 0; qq < TN / NSVC; qq++) {
-                    const int r = warp + NSVC * qq;
-                    if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_s[r] * D + 4 * lane));
-                }
+                for (int half = 0; half < 2; half++) {
+                    float4 xv[8];
 #pragma unroll
-                for (int qq = 0; qq < TN / NSVC; qq++) {
-                    const int r = warp + NSVC * qq;
-                    if (r < n) {
-                        const float4 x = xv[qq];
-                        const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
-                        const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y),
-                                                      umma::tf32_round(df.z), umma::tf32_round(df.w));
-                        const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
-                                                      umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
-                        const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
-                        *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
-                        *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
+                    for (int qq = 0; qq < 8; qq++) {
+                        const int r = warp + NSVC * (half * 8 + qq);
+                        if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_s[r] * D + 4 * lane));
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < 8; qq++) {
+                        const int r = warp + NSVC * (half * 8 + qq);
+                        if (r < n) {
+                            const float4 x = xv[qq];
+                            const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+                            const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y),
+                                                          umma::tf32_round(df.z), umma::tf32_round(df.w));
+                            const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
+                                                          umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
+                            const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
+                            *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
+                            *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
+                        }
                     }
                 }
             }
             umma::fence_proxy_async_smem();
             svc_barrier();
+            lap(2);
             if (warp == 0) {
                 if (a_pending) {
                     umma::mbar_wait(bar_a, par_a);
@@ -244,9 +295,13 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 __syncwarp();
             }
             a_pending = false;
+            // the tile's slot list moves to registers: pick[] and (after the barriers inside) nothing else is reused, but
+            // the NEXT tile is chosen and claimed now, while the tensor cores work on this one
+            choose_and_claim();
             umma::mbar_wait(bar_mma, par_m);
             par_m ^= 1;
             umma::tc_fence_after();
+            lap(3);
             // ---- epilogue: service warp w reads TMEM lanes 32w..32w+31 (output coordinates), 16 requests at a time; the
             // slot receives Y itself, the requester applies its responsibility ------------------------------------------------
             const int a = 32 * warp + lane;
@@ -261,19 +316,18 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
             umma::tc_fence_before();
             svc_barrier();  // all four coordinate quarters of every result row are written ...
+            lap(4);
             if (tid < n) red_release_add_u32(P.done + slot_s[tid] / (uint32_t)P.vslots, 1u);  // ... before the counter moves
             tiles++;
             rows_served += n;
-            if (++streak >= 8 && nq > 1) {  // fairness among the queues of a CTA that owns several
-                streak = 0;
-                qi = (qi + 1) % nq;
-            }
-            svc_barrier();  // row_s / slot_s / pre are free for the next tile
+            svc_barrier();  // row_s / slot_s are free for the next tile
+            lap(5);
         }
         if (P.stats && tid == 0) {
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 0), (unsigned long long)tiles);
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 1), (unsigned long long)rows_served);
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 2), (unsigned long long)idle_polls);
+            for (int k = 0; k < 6; k++) atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 8 + k), (unsigned long long)ph[k]);
         }
     } else {
         // =============================== WALKER WARPS ====================================================================
@@ -286,7 +340,6 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         const int64_t gwarp = (int64_t)blockIdx.x * NWALK + ww;
         const bool walker = gwarp < P.active_warps;
         const int64_t slot0 = gwarp * P.vslots;
-        const int rep = (int)(gwarp % P.n_rep);
         fused::SgnsArgs SA;
         SA.node = P.node; SA.ctx = P.ctx; SA.table = P.table; SA.mod = P.mod; SA.mu = P.mu; SA.inv_cov = P.inv_cov;
         SA.weight = P.weight; SA.pi = nullptr; SA.ybuf = P.ybuf; SA.K = K; SA.dense = false; SA.o3_on = true;
@@ -364,7 +417,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                     const unsigned peers = __match_any_sync(FULL, key);
                     if (key >= 0) {
                         const int leader = __ffs(peers) - 1;
-                        const int q = c * P.n_rep + rep;
+                        const int q = c;
                         unsigned basep = 0;
                         if (lane == leader) basep = atomicAdd(P.tail + q * 8, (unsigned)__popc(peers));
                         basep = __shfl_sync(peers, basep, leader);
@@ -462,10 +515,8 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     if (comemb_opts().max_warps > 0 && comemb_opts().max_warps < warps) warps = comemb_opts().max_warps;
     if (n_walks < warps) warps = n_walks;
     const int grid = (int)((warps + NWALK - 1) / NWALK);
-    int n_rep = (grid + K - 1) / K;  // replicas per community so that every SM's service warps own a queue
-    n_rep = n_rep < 1 ? 1 : (n_rep > 4 ? 4 : n_rep);
-    const int Q = K * n_rep;
-    if ((Q + grid - 1) / grid > MAXQ) return COMEMB_E_UNSUPPORTED;
+    const int n_rep = 1, Q = K;  // one queue per community, served by whichever CTAs find it the fullest
+    if (Q > 2047) return COMEMB_E_UNSUPPORTED;
     const int64_t total_warps = (int64_t)grid * NWALK;
     const int vslots = 2 * window;
     // a walker has at most vslots requests in flight, so total_warps * vslots bounds the entries of one queue that are
@@ -478,7 +529,7 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
         off = (off + bytes + 1023) & ~(size_t)1023;
         return at;
     };
-    const size_t sz_ctl = 256 + (size_t)Q * 32 + (size_t)total_warps * 4;
+    const size_t sz_ctl = 256 + (size_t)Q * 64 + (size_t)total_warps * 4;
     const size_t o_ctl = carve(sz_ctl), o_y = carve((size_t)total_warps * vslots * D * 4);
     const size_t o_ring = carve((size_t)Q * cap * 8), o_img = carve((size_t)K * A_IMG_BYTES);
     if (off > ((size_t)24 << 30)) return COMEMB_E_UNSUPPORTED;
@@ -507,13 +558,14 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     P.err = reinterpret_cast<int *>(scratch + o_ctl + 32);
     P.live = reinterpret_cast<int *>(scratch + o_ctl + 48);
     P.tail = reinterpret_cast<unsigned *>(scratch + o_ctl + 256);
-    P.done = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 32);
+    P.claim = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 32);
+    P.done = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 64);
     P.cap = cap; P.n_rep = n_rep; P.Q = Q; P.vslots = vslots; P.active_warps = warps;
     static const bool want_stats = getenv("COMEMB_ROUND_STATS") != nullptr;
     long long *d_stats = nullptr;
     if (want_stats) {
-        cudaMalloc(&d_stats, 8 * sizeof(long long));
-        cudaMemset(d_stats, 0, 8 * sizeof(long long));
+        cudaMalloc(&d_stats, 16 * sizeof(long long));
+        cudaMemset(d_stats, 0, 16 * sizeof(long long));
     }
     P.stats = d_stats;
     switch (negative) {
@@ -526,7 +578,7 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
         default: e = launch_async_t<7>(P, atomic, grid, st); break;
     }
     if (want_stats) {
-        long long h[8];
+        long long h[16];
         int h_err = 0;
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
@@ -537,6 +589,8 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
                 "cycles: stage %lld wait %lld sgns %lld (centres %lld)\n",
                 grid, n_rep, Q, h_err, h[0], h[1], h[0] ? (double)h[1] / h[0] : 0.0, h[2], h[3] / (h[6] + 1),
                 h[4] / (h[6] + 1), h[5] / (h[6] + 1), h[6]);
+        fprintf(stderr, "[async stats] service cycles per tile: probe %lld pop %lld gather %lld mma %lld epilogue %lld signal %lld\n",
+                h[8] / (h[0] + 1), h[9] / (h[0] + 1), h[10] / (h[0] + 1), h[11] / (h[0] + 1), h[12] / (h[0] + 1), h[13] / (h[0] + 1));
     }
     cudaFreeAsync(scratch, st);
     return (int)e;
