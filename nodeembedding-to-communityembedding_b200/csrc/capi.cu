@@ -92,6 +92,15 @@ int comemb_init(void) {
     if (dev < 0 || dev >= MAX_DEVICES) return COMEMB_E_ARG;
     if (!g_lut_dev[dev]) CUDA_TRY(cudaMalloc(&g_lut_dev[dev], sizeof(g_host_lut)));
     CUDA_TRY(cudaMemcpy(g_lut_dev[dev], g_host_lut, sizeof(g_host_lut), cudaMemcpyHostToDevice));
+    {   // the launchers take stream-ordered scratch (cudaMallocAsync): keep the pool's memory across calls instead of
+        // returning it to the driver at every synchronisation (the default release threshold is 0)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = 2ull << 30, cur = 0;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+            if (cur < keep) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     return 0;
 }
