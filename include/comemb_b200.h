@@ -141,6 +141,14 @@ int comemb_o3_batch(float *d_node, int64_t n_rows, int size, const uint32_t *d_r
 int comemb_o3_batch_top1(float *d_node, int64_t n_rows, int size, const uint32_t *d_rows, int64_t n_sel,
                          const float *d_mu, const float *d_inv_cov_t, const int32_t *d_comm, const float *d_weight, int K,
                          double beta, float lr, int iters, void *stream);
+/* ---- GMM E-step: the distance part of Community2Vec.fit's GaussianMixture (ADSCModel/community_embeddings.py:16-37;
+ * sklearn _estimate_log_gaussian_prob, covariance_type 'full') -----------------------------------------------------------------
+ *    d_sq[n][k] = || x_n . P_k - mu_k . P_k ||^2      P_k = d_prec_chol[k] (precision Cholesky factor, [size][size]),
+ *                                                     d_bias[k] = mu_k . P_k  ([K][size])
+ * size 128: tcgen05 3xTF32 tiles with P_k resident in shared memory, the squared norm reduced in the epilogue -- only the
+ * [n, K] result reaches memory.  Other sizes: COMEMB_E_UNSUPPORTED (the caller uses a library GEMM). */
+int comemb_gmm_estep(const float *d_x, int64_t n, int size, const float *d_prec_chol, const float *d_bias, int K,
+                     float *d_sq, void *stream);
 /* out[k][b][a] = in[k][a][b] for K blocks of size x size */
 int comemb_transpose_blocks(const float *d_in, float *d_out, int K, int size, void *stream);
 

@@ -4,10 +4,12 @@ The reference fits `sklearn.mixture.GaussianMixture(k, 'full', n_init=10, reg_co
 (ADSCModel/community_embeddings.py:16-37); at 100K x 128 points and K=50 that is minutes per fit and dominates an
 outer iteration once o1/o2/o3 run at GPU speed.  This class restates sklearn's EM step by step
 (sklearn/mixture/_gaussian_mixture.py: `_estimate_gaussian_parameters`, `_compute_precision_cholesky`,
-`_estimate_log_gaussian_prob`, `_e_step`/`_m_step`, lower bound, `tol` on its change) on torch tensors: the heavy parts
-are plain library GEMMs (E-step: [N,d] x [d,K*d], all components at once; covariances: batched [kc,d,N] x [kc,N,d];
-cuBLAS) and batched Cholesky / triangular solves (cuSOLVER / cuBLAS) -- 4*N*K*d^2 flop per iteration (0.33 TFLOP at
-N=100K, K=50, d=128; 14 ms per EM iteration on a B200 in fp32, scripts/gmm_profile.py).  No hand-written kernel here, by design: these are library-shaped dense operations, not part of the SGD path.
+`_estimate_log_gaussian_prob`, `_e_step`/`_m_step`, lower bound, `tol` on its change) on torch tensors.  The
+E-step -- the dominant 2*N*K*d^2 contraction -- is the hand-written tcgen05 kernel comemb_gmm_estep at d == 128 in fp32
+(csrc/o3_gemm.cu: P_k resident in shared memory as the 3xTF32 A operand, points streamed as 64-row tiles, squared norm
+reduced in the epilogue, only [N, K] written); the fallback (other sizes, float64, CPU) is one library GEMM [N,d] x [d,K*d]
+per row block.  The M-step's covariances are batched library GEMMs ([kc,d,N] x [kc,N,d]; cuBLAS) and the precision factors
+batched Cholesky / triangular solves (cuSOLVER / cuBLAS).
 
 Parity: given the same initial responsibilities the iterations follow sklearn's to fp32 round-off
 (tests/test_gmm_device.py, CPU and GPU).  The initialisation differs (own k-means++ / Lloyd instead of sklearn's KMeans
@@ -20,7 +22,7 @@ import numpy as np
 
 class DeviceGaussianMixture(object):
     def __init__(self, n_components=1, reg_covar=1e-6, tol=1e-3, max_iter=100, n_init=1, random_state=None,
-                 dtype=None, kmeans_iter=20, workspace_bytes=6 << 30, tf32=False, sparse_m_step=True):
+                 dtype=None, kmeans_iter=20, workspace_bytes=6 << 30, tf32=False, sparse_m_step=True, estep_kernel=True):
         self.n_components = int(n_components)
         self.reg_covar = float(reg_covar)
         self.tol = float(tol)
@@ -31,6 +33,7 @@ class DeviceGaussianMixture(object):
         self.kmeans_iter = kmeans_iter
         self.workspace_bytes = int(workspace_bytes)  # bound on the temporaries of the batched E / M steps
         self.sparse_m_step = bool(sparse_m_step)
+        self.estep_kernel = bool(estep_kernel)  # fp32, d == 128 on CUDA: the tcgen05 E-step kernel instead of the library GEMM
         self.tf32 = bool(tf32)  # let cuBLAS use TF32 tensor cores for the fp32 GEMMs (about 1.7x per EM iteration;
         #                         the sklearn comparison of tests/test_gmm_device.py holds for tf32=False)
         self.converged_ = False
@@ -105,11 +108,20 @@ class DeviceGaussianMixture(object):
         Pcat = P.permute(1, 0, 2).reshape(d, K * d)
         b_neg = -torch.bmm(self.means_[:, None, :], P).reshape(1, K * d)
         log_prob = torch.empty((n, K), dtype=X.dtype, device=X.device)
-        rows = max(1, int(self.workspace_bytes // (K * d * X.element_size())))
-        for n0 in range(0, n, rows):
-            y = torch.addmm(b_neg, X[n0:n0 + rows], Pcat)  # X @ Pcat - b, the bias added in the GEMM epilogue
-            log_prob[n0:n0 + rows] = torch.linalg.vector_norm(y.view(-1, K, d), dim=2).square_()  # one pass over y
-            del y
+        if self.estep_kernel and X.is_cuda and X.dtype == torch.float32 and d == 128 and n > 0:
+            # hand-written E-step (csrc/o3_gemm.cu, comemb_gmm_estep): tcgen05 3xTF32 tiles, P_k resident in shared
+            # memory, squared norm reduced in the epilogue -- no [rows, K*d] product is ever written
+            from .. import _lib
+            xc, pc, bias = X.contiguous(), P.contiguous(), (-b_neg).reshape(K, d).contiguous()
+            with torch.cuda.device(X.device):
+                _lib.check(_lib.load().comemb_gmm_estep(_lib.ptr(xc), n, d, _lib.ptr(pc), _lib.ptr(bias), K,
+                                                        _lib.ptr(log_prob), _lib.stream_ptr()))
+        else:
+            rows = max(1, int(self.workspace_bytes // (K * d * X.element_size())))
+            for n0 in range(0, n, rows):
+                y = torch.addmm(b_neg, X[n0:n0 + rows], Pcat)  # X @ Pcat - b, the bias added in the GEMM epilogue
+                log_prob[n0:n0 + rows] = torch.linalg.vector_norm(y.view(-1, K, d), dim=2).square_()  # one pass over y
+                del y
         weighted = -0.5 * (d * math.log(2 * math.pi) + log_prob) + log_det + torch.log(self.weights_)
         norm = torch.logsumexp(weighted, dim=1)
         return norm, weighted - norm[:, None]

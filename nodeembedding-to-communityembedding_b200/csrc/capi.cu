@@ -30,6 +30,7 @@ int launch_sg_twin(float *, float *, int, const uint32_t *, const uint32_t *, in
 int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const float *, const float *, const float *,
                     const int32_t *, const float *, int, double, float, int, cudaStream_t);
 int launch_transpose_blocks(const float *, float *, int, int, cudaStream_t);
+int launch_gmm_estep(const float *, int64_t, const float *, const float *, int, float *, cudaStream_t);
 int launch_scale(float *, int64_t, float, cudaStream_t);
 int launch_o2_pos_loss(const float *, const float *, int, const uint32_t *, const int64_t *, int64_t, int, double *,
                        cudaStream_t);
@@ -251,6 +252,13 @@ int comemb_o3_batch_top1(float *d_node, int64_t n_rows, int size, const uint32_t
     if (n_sel < 0) return COMEMB_E_ARG;
     return launch_o3_batch(d_node, n_rows, size, d_rows, n_sel, d_mu, d_inv_cov_t, nullptr, d_comm, d_weight, K, beta, lr,
                            iters, (cudaStream_t)stream);
+}
+
+int comemb_gmm_estep(const float *d_x, int64_t n, int size, const float *d_prec_chol, const float *d_bias, int K,
+                     float *d_sq, void *stream) {
+    if (!d_x || !d_prec_chol || !d_bias || !d_sq || n < 0 || K <= 0) return COMEMB_E_ARG;
+    if (size != 128) return COMEMB_E_UNSUPPORTED;
+    return launch_gmm_estep(d_x, n, d_prec_chol, d_bias, K, d_sq, (cudaStream_t)stream);
 }
 
 int comemb_transpose_blocks(const float *d_in, float *d_out, int K, int size, void *stream) {

@@ -300,3 +300,187 @@ int launch_o3_gemm(float *node, const uint32_t *rows, int64_t n_sel, const float
     cudaFreeAsync(scratch, st);
     return (int)e;
 }
+
+// ==== GMM E-step (sklearn _estimate_log_gaussian_prob, 'full'):  sq[n][k] = || x_n . P_k - mu_k . P_k ||^2 =========
+// The same contraction with A = P_k^T (precision Cholesky factor, resident hi/lo TF32 images) and B = 64 consecutive points:
+// D[j][n] = sum_b P_k[b][j] x_n[b] in TMEM; the epilogue subtracts bias[k][j] = (mu_k . P_k)[j], squares, and reduces over
+// the 128 output coordinates j (= TMEM lanes = threads) with a transposed shuffle reduction, so only the [N, K] matrix of
+// squared norms ever reaches memory (the library formulation materialises the [N, K*d] product).  Jobs (k, tile) are
+// walked by persistent CTAs in k-major order: P_k is fetched (TMA bulk copy) once per CTA and component.
+namespace {
+
+// 16 values per lane, summed over the 32 lanes: 8+4+2+1+1 shuffles.  On return the lanes whose bit 0 is clear hold the total of
+// column ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
+__device__ __forceinline__ float reduce16_transposed(const float (&v)[16], int lane) {
+    float r8[8], r4[4], r2[2];
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r8[i] = (b16 ? v[8 + i] : v[i]) + __shfl_xor_sync(FULL, b16 ? v[i] : v[8 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; i++) r4[i] = (b8 ? r8[4 + i] : r8[i]) + __shfl_xor_sync(FULL, b8 ? r8[i] : r8[4 + i], 8);
+#pragma unroll
+    for (int i = 0; i < 2; i++) r2[i] = (b4 ? r4[2 + i] : r4[i]) + __shfl_xor_sync(FULL, b4 ? r4[i] : r4[2 + i], 4);
+    float t = (b2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, b2 ? r2[0] : r2[1], 2);
+    t += __shfl_xor_sync(FULL, t, 1);
+    return t;
+}
+
+struct EstepParams {
+    const float *x;
+    int64_t n;
+    int K;
+    const char *a_img;
+    const float *bias;  // [K][128] = mu_k . P_k
+    float *sq;          // [n][K]
+};
+
+template <int TN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) gmm_estep_kernel(const EstepParams P) {
+    using L = O3GemmSmem<TN>;
+    static_assert(TN == 64 && WARPS % 4 == 0, "tile shape");
+    constexpr uint32_t TMEM_COLS = 64;
+    extern __shared__ char smem_raw[];
+    char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *bias_s = reinterpret_cast<float *>(smem + L::MU);     // [128]
+    float *part_s = reinterpret_cast<float *>(smem + ((L::TOTAL + 15) & ~15));  // [TN][4] partial sums per TMEM lane quarter
+    uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) umma::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x == 0) {
+        umma::mbar_init(bar_a, 1);
+        umma::mbar_init(bar_mma, 1);
+        umma::fence_mbar_init();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t taddr = *tmem_slot;
+    const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
+    const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
+    const int64_t tiles = (P.n + TN - 1) / TN, n_jobs = tiles * P.K;
+    const int64_t j0 = n_jobs * blockIdx.x / gridDim.x, j1 = n_jobs * (blockIdx.x + 1) / gridDim.x;
+    int cur_k = -1;
+    uint32_t par_a = 0, par_m = 0;
+    bool a_pending = false;
+    constexpr int RPW = (TN + WARPS - 1) / WARPS;
+    float4 xv[RPW];
+    auto prefetch = [&](int64_t job) {  // the tile's rows are consecutive: coalesced, all in flight at once
+        const int64_t r0 = (job % tiles) * TN;
+#pragma unroll
+        for (int q = 0; q < RPW; q++) {
+            const int64_t r = r0 + warp + q * WARPS;
+            xv[q] = (warp + q * WARPS < TN && r < P.n) ? __ldg(reinterpret_cast<const float4 *>(P.x + r * D + 4 * lane))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (j0 < j1) prefetch(j0);
+    for (int64_t j = j0; j < j1; j++) {
+        const int k = (int)(j / tiles);
+        const int64_t r0 = (j % tiles) * TN;
+        const int cnt = (int)min((int64_t)TN, P.n - r0);
+        const int n16 = (cnt + 15) & ~15;
+        if (k != cur_k) {
+            if (threadIdx.x == 0) {
+                umma::mbar_expect_tx(bar_a, A_IMG_BYTES);
+                const char *src = P.a_img + (int64_t)k * A_IMG_BYTES;
+#pragma unroll
+                for (int q = 0; q < 8; q++) umma::bulk_g2s(smem + L::A_HI + q * 16384, src + q * 16384, 16384, bar_a);
+            }
+            if (warp == 1) *reinterpret_cast<float4 *>(bias_s + 4 * lane) =
+                __ldg(reinterpret_cast<const float4 *>(P.bias + (int64_t)k * D + 4 * lane));
+            a_pending = true;
+            cur_k = k;
+        }
+#pragma unroll
+        for (int q = 0; q < RPW; q++) {
+            const int r = warp + q * WARPS;
+            if (r < TN) {
+                const float4 x = xv[q];
+                const float4 hi = make_float4(umma::tf32_round(x.x), umma::tf32_round(x.y), umma::tf32_round(x.z),
+                                              umma::tf32_round(x.w));
+                const float4 lo = make_float4(umma::tf32_round(x.x - hi.x), umma::tf32_round(x.y - hi.y),
+                                              umma::tf32_round(x.z - hi.z), umma::tf32_round(x.w - hi.w));
+                const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
+                *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
+                *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
+            }
+        }
+        umma::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            if (a_pending) {
+                umma::mbar_wait(bar_a, par_a);
+                par_a ^= 1;
+            }
+            umma::tc_fence_after();
+            if (lane == 0) {
+                umma::issue_3xtf32(taddr, a_hi, a_lo, b_hi, b_lo, TN, n16);
+                umma::mma_commit(bar_mma);
+            }
+            __syncwarp();
+        }
+        a_pending = false;
+        if (j + 1 < j1) prefetch(j + 1);  // the next tile's rows travel while the tensor cores work
+        umma::mbar_wait(bar_mma, par_m);
+        par_m ^= 1;
+        umma::tc_fence_after();
+        // epilogue: thread = output coordinate jj of TMEM lane quarter (warp % 4); warps with the same quarter share the chunks
+        const int jj = 32 * (warp & 3) + lane;
+        const float bj = bias_s[jj];
+        for (int ch = warp >> 2; ch * 16 < n16; ch += WARPS / 4) {
+            float v[16];
+            umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ch * 16), v);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const float y = v[q] - bj;
+                v[q] = y * y;
+            }
+            const float tot = reduce16_transposed(v, lane);
+            if (!(lane & 1)) {
+                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                part_s[(ch * 16 + col) * 4 + (warp & 3)] = tot;
+            }
+        }
+        umma::tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const float4 p = *reinterpret_cast<const float4 *>(part_s + 4 * threadIdx.x);
+            P.sq[(r0 + threadIdx.x) * P.K + k] = (p.x + p.y) + (p.z + p.w);
+        }
+        __syncthreads();  // part_s, the B images and the accumulator are free again
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(taddr, TMEM_COLS);
+}
+
+}  // namespace
+
+// d_x [n][128], d_prec_chol [K][128][128] (P_k as sklearn stores it), d_bias [K][128] = mu_k . P_k, d_sq [n][K] (out)
+int launch_gmm_estep(const float *d_x, int64_t n, const float *d_prec_chol, const float *d_bias, int K, float *d_sq,
+                     cudaStream_t st) {
+    constexpr int TN = 64, WARPS = 16;
+    using L = O3GemmSmem<TN>;
+    if (n <= 0 || K <= 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    char *img = nullptr;
+    CUDA_TRY(cudaMallocAsync(&img, (size_t)K * A_IMG_BYTES, st));
+    int r = launch_umma_prep_a(d_prec_chol, img, K, st);
+    if (r) {
+        cudaFreeAsync(img, st);
+        return r;
+    }
+    EstepParams P;
+    P.x = d_x; P.n = n; P.K = K; P.a_img = img; P.bias = d_bias; P.sq = d_sq;
+    const int smem = L::TOTAL + 1024 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gmm_estep_kernel<TN, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) {
+        const int64_t jobs = ((n + TN - 1) / TN) * K;
+        gmm_estep_kernel<TN, WARPS><<<(int)(jobs < sms ? jobs : sms), WARPS * 32, smem, st>>>(P);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(img, st);
+    return (int)e;
+}

@@ -136,3 +136,47 @@ def test_community2vec_fit_device_backend_feeds_o3(golden):
     # the step pulls nodes towards their component means
     mu = m.centroid[m.pi.argmax(1)]
     assert ((m.node_embedding - mu).norm(dim=1) < (before - mu).norm(dim=1) + 1e-6).float().mean() > 0.95
+
+
+@pytest.mark.gpu
+def test_estep_kernel_matches_library_form_and_sklearn_at_d128():
+    """comemb_gmm_estep (tcgen05 3xTF32 tiles, squared norm reduced in the epilogue) at d = 128: the [N, K] matrix of
+    squared Mahalanobis norms against a float64 evaluation of the same formula (<= 1e-5 relative to the row maximum: the
+    expression x.P - mu.P cancels, any fp32 evaluation carries that), ragged N (not a multiple of the 64-row tile),
+    K = 1 and K > number of SMs' worth of jobs; then five EM iterations from identical responsibilities against sklearn's
+    own float32 EM like the library path."""
+    import torch
+    from sklearn.mixture import GaussianMixture
+    from comemb_b200 import _lib
+    from comemb_b200.ADSCModel.gmm_device import DeviceGaussianMixture
+    rs = np.random.RandomState(4)
+    for n, K in ((1, 1), (63, 2), (1000, 5), (4099, 7)):
+        d = 128
+        x = rs.normal(size=(n, d)).astype(np.float32)
+        mu = rs.normal(size=(K, d)).astype(np.float32) * 0.5
+        P = (np.triu(rs.normal(size=(K, d, d))) * 0.05 + np.eye(d)).astype(np.float32)  # upper triangular like sklearn's
+        bias = np.einsum("kb,kbj->kj", mu.astype(np.float64), P.astype(np.float64)).astype(np.float32)
+        want = ((np.einsum("nb,kbj->nkj", x.astype(np.float64), P.astype(np.float64)) - bias[None].astype(np.float64)) ** 2).sum(2)
+        dx, dP, db = (torch.as_tensor(a, device="cuda") for a in (x, P, bias))
+        out = torch.full((n, K), -1.0, device="cuda")
+        _lib.check(_lib.load().comemb_gmm_estep(dx.data_ptr(), n, d, dP.data_ptr(), db.data_ptr(), K, out.data_ptr(), None))
+        got = out.cpu().numpy()
+        assert np.abs(got - want).max() <= 1e-5 * want.max(), (n, K, np.abs(got - want).max(), want.max())
+    x, lab = _blobs(3000, 128, 4, 9)
+    x = x.astype(np.float32)
+    resp = rs.rand(3000, 4).astype(np.float32) ** 3
+    resp /= resp.sum(1, keepdims=True)
+    sk = GaussianMixture(n_components=4, covariance_type="full", reg_covar=1e-4, tol=0.0, max_iter=5)
+    sk._initialize(x, resp)
+    for _ in range(5):
+        log_prob_norm, log_resp = sk._e_step(x)
+        sk._m_step(x, log_resp)
+    res = {}
+    for kern in (True, False):
+        gm = DeviceGaussianMixture(n_components=4, reg_covar=1e-4, tol=0.0, max_iter=5, estep_kernel=kern)
+        gm.fit(torch.as_tensor(x, device="cuda"), resp_init=torch.as_tensor(resp, device="cuda"))
+        res[kern] = gm
+        assert abs(gm.lower_bound_ - float(log_prob_norm)) <= 2e-3 * abs(float(log_prob_norm))
+        for got, want in ((gm.means_, sk.means_), (gm.covariances_, sk.covariances_)):
+            assert np.abs(got.cpu().numpy() - want).max() <= 2e-3 * max(1.0, np.abs(want).max())
+    assert abs(res[True].lower_bound_ - res[False].lower_bound_) <= 1e-4 * abs(res[False].lower_bound_)
