@@ -1,5 +1,8 @@
 """Quality evaluators for the Hogwild acceptance tests: community NMI and node-classification
-micro-F1 on the learned node table, and the o1 / o2 objectives.  Host-side (sklearn); not part of the SGD path."""
+micro-F1 on the learned node table, and the o1 / o2 objectives.  The objectives run on the device (Node2Vec.loss,
+comemb_o2_pos_loss; pinned against reference-generated values in tests/golden/golden_losses.json); `nmi` and
+`community_nmi(method="device")` keep the node table on the device as well (k-means assignment + contingency table in
+torch); the micro-F1 protocol (one-vs-rest logistic regression) is host-side sklearn.  Not part of the SGD path."""
 import numpy as np
 
 
@@ -7,14 +10,44 @@ def _np(x):
     return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
 
 
+def nmi(labels_true, labels_pred):
+    """Normalised mutual information (arithmetic-mean normalisation, sklearn's default) of two labelings given as integer
+    tensors / arrays -- computed with torch on whatever device `labels_pred` lives on (contingency table by bincount)."""
+    import torch
+    b = labels_pred if isinstance(labels_pred, torch.Tensor) else torch.as_tensor(np.asarray(labels_pred))
+    a = torch.as_tensor(np.asarray(_np(labels_true))).to(b.device)
+    a = torch.unique(a.long(), return_inverse=True)[1]
+    b = torch.unique(b.long(), return_inverse=True)[1]
+    ka, kb, n = int(a.max()) + 1, int(b.max()) + 1, a.numel()
+    cont = torch.bincount(a * kb + b, minlength=ka * kb).reshape(ka, kb).double()
+    pa, pb, pab = cont.sum(1) / n, cont.sum(0) / n, cont / n
+    nz = pab > 0
+    mi = (pab[nz] * (pab[nz].log() - (pa[:, None] * pb[None, :])[nz].log())).sum()
+    ha = -(pa[pa > 0] * pa[pa > 0].log()).sum()
+    hb = -(pb[pb > 0] * pb[pb > 0].log()).sum()
+    denom = 0.5 * (ha + hb)
+    if float(denom) <= 0.0:
+        return 1.0  # both labelings are constant
+    return float((mi / denom).clamp(min=0.0))
+
+
 def community_nmi(embedding, labels, k=None, method="gmm", seed=0):
     """NMI between ground-truth communities and a clustering of the node table.  method="gmm" mirrors the reference's
     community assignment (GaussianMixture, community_embeddings.py:16-37, diagonal covariance for d >> n robustness);
-    "kmeans" is the cheaper proxy used on large graphs."""
+    "kmeans" is the cheaper proxy used on large graphs; "device" = k-means++/Lloyd assignment and the NMI itself on the
+    device the table lives on (nothing is copied to the host)."""
+    labels = np.asarray(_np(labels))
+    k = int(k or len(np.unique(labels)))
+    if method == "device":
+        import torch
+        from .ADSCModel.gmm_device import DeviceGaussianMixture
+        x = embedding if isinstance(embedding, torch.Tensor) else torch.as_tensor(np.asarray(embedding))
+        gen = torch.Generator(device=x.device)
+        gen.manual_seed(int(seed))
+        one = DeviceGaussianMixture(n_components=k, kmeans_iter=30)._kmeans_resp(x.float(), gen)
+        return nmi(labels, one.argmax(1))
     from sklearn.metrics import normalized_mutual_info_score
     x = _np(embedding).astype(np.float64)
-    labels = np.asarray(labels)
-    k = int(k or len(np.unique(labels)))
     if method == "kmeans":
         from sklearn.cluster import KMeans
         pred = KMeans(k, n_init=5, random_state=seed).fit_predict(x)

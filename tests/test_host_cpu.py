@@ -302,3 +302,39 @@ def test_graph_rows_are_remapped_to_table_rows():
     m2.device, m2._id_index = "cpu", None
     m2.vocab = {i: Vocab(count=2, index=i - 1, sample_probability=1.0) for i in (1, 2, 3)}
     assert m2.graph_row_lut(G2) is None and m2.walks_to_rows(G2, walks) is walks
+
+
+def test_node2vec_loss_matches_the_reference_value():
+    """Node2Vec.loss against values produced by the REFERENCE's own Node2Vec.loss (node_embeddings.py:26-31) on its own
+    karate tables (tests/golden/make_golden_losses.py -> golden_losses.json): initial table, after the pre-training o1
+    epoch, after the first full iteration.  The reference sums in float32, we sum in float64: 1e-5 relative."""
+    import json
+    import torch
+    from comemb_b200.ADSCModel.model import Model
+    from comemb_b200.ADSCModel.node_embeddings import Node2Vec
+    from comemb_b200.utils.embedding import Vocab
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_losses.json")))["node2vec_loss"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_karate.npz"))
+    m = Model.__new__(Model)
+    m.device, m._id_index = "cpu", None
+    m.vocab = {i + 1: Vocab(count=int(c), index=i, sample_probability=1.0) for i, c in enumerate(g["degrees"])}
+    for stage, ref in want.items():
+        m.node_embedding = torch.from_numpy(g[stage])
+        got = Node2Vec(workers=1, negative=4, lr=0.1).loss(m, g["edges"])
+        assert abs(got - ref) <= 1e-5 * abs(ref), (stage, got, ref)
+    assert want["init_node"] > want["pre_o1_node"] > want["it0_o2_node"]  # the reference's own training lowers it
+
+
+def test_nmi_on_tensors_matches_sklearn():
+    import torch
+    from sklearn.metrics import normalized_mutual_info_score
+    from comemb_b200 import evaluation
+    rs = np.random.RandomState(0)
+    for ka, kb, n in ((2, 2, 34), (5, 7, 1000), (50, 50, 20000), (1, 3, 10)):
+        a, b = rs.randint(0, ka, n), rs.randint(0, kb, n)
+        b[: n // 2] = a[: n // 2] % kb  # correlated halves
+        assert abs(evaluation.nmi(a, torch.as_tensor(b)) - normalized_mutual_info_score(a, b)) < 1e-9
+    assert evaluation.nmi(np.arange(10) % 2, torch.as_tensor((np.arange(10) % 2) * 5 + 1)) == pytest.approx(1.0)
+    x = np.concatenate([rs.normal(size=(200, 8)) + 6 * rs.normal(size=(1, 8)) for _ in range(4)])
+    lab = np.repeat(np.arange(4), 200)
+    assert evaluation.community_nmi(torch.as_tensor(x, dtype=torch.float32), lab, method="device") > 0.9
