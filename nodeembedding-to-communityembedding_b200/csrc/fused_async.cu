@@ -167,41 +167,61 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         // itself).  Result in pick[]; count 0 = nothing claimed, -1 = every walker has finished and all queues are empty.
         auto choose_and_claim = [&]() {
             const int live = tid == 0 ? *reinterpret_cast<volatile int *>(P.live) : 1;  // read BEFORE the queues
-            int key = 0;
+            int key = 0, my_backlog = 0;
+            unsigned my_h = 0;
             for (int q = tid; q < P.Q; q += NSVC * 32) {
-                const int backlog = (int)(ld_vol(P.tail + q * 8) - ld_vol(P.claim + q * 8));
+                const unsigned h = ld_vol(P.claim + q * 8);
+                const int backlog = (int)(ld_vol(P.tail + q * 8) - h);
                 if (backlog > 0) {
                     // + a CTA-specific tie-breaker so that the CTAs do not all rush to the same queue
                     const int score = min(backlog, 1 << 19) + (q == cur_c ? (3 * TN) / 2 : 0) + ((q * 7 + (int)blockIdx.x * 13) & 31);
-                    key = max(key, (score << 11) | q);
+                    const int k2 = (score << 11) | q;
+                    if (k2 > key) {
+                        key = k2;
+                        my_h = h;
+                        my_backlog = backlog;
+                    }
                 }
             }
+            int best = key;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) key = max(key, __shfl_xor_sync(FULL, key, o));
-            if (lane == 0) wbest[warp] = key;
+            for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+            if (lane == 0) wbest[warp] = best;
             svc_barrier();
-            if (tid == 0) {
-                int k = max(max(wbest[0], wbest[1]), max(wbest[2], wbest[3]));
-                int n = 0, q = 0;
-                unsigned h = 0;
-                if (k > 0) {
-                    q = k & 2047;
-                    for (int attempt = 0; attempt < 3 && n == 0; attempt++) {
-                        h = ld_vol(P.claim + q * 8);
-                        const int backlog = (int)(ld_vol(P.tail + q * 8) - h);
-                        if (backlog <= 0) break;
-                        const int want = min(backlog, TN);
-                        if (atomicCAS(P.claim + q * 8, h, h + (unsigned)want) == h) n = want;
+            const int k = max(max(wbest[0], wbest[1]), max(wbest[2], wbest[3]));
+            if (k > 0 && key == k) {  // the one thread that saw the winning queue claims from what it saw (no re-read)
+                const int q = k & 2047;
+                int n = 0;
+                unsigned h = my_h;
+                int backlog = my_backlog;
+                for (int attempt = 0; attempt < 3 && n == 0 && backlog > 0; attempt++) {
+                    const int want = min(backlog, TN);
+                    const unsigned old = atomicCAS(P.claim + q * 8, h, h + (unsigned)want);
+                    if (old == h) {
+                        n = want;
+                    } else {  // another CTA claimed meanwhile: retry from what the CAS returned
+                        h = old;
+                        backlog = (int)(ld_vol(P.tail + q * 8) - h);
                     }
-                    empty_scans = 0;
-                } else if (live == 0) {
-                    if (++empty_scans >= 2) n = -1;
-                } else {
-                    empty_scans = 0;
                 }
                 pick[0] = q;
                 pick[1] = (int)h;
                 pick[2] = n;
+            }
+            if (tid == 0) {
+                if (k > 0) {
+                    empty_scans = 0;
+                } else {
+                    int n = 0;
+                    if (live == 0) {
+                        if (++empty_scans >= 2) n = -1;
+                    } else {
+                        empty_scans = 0;
+                    }
+                    pick[0] = 0;
+                    pick[1] = 0;
+                    pick[2] = n;
+                }
             }
             svc_barrier();
         };
@@ -221,8 +241,12 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             const int c = q;
             const int n16 = (n + 15) & ~15;
             if (tid < n) {  // the claimed entries are reserved, hence published within moments: take them, free the positions
-                unsigned long long *p = P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1));
-                unsigned long long e = ld_acquire_u64(p);
+                // Relaxed (volatile) loads: everything read on behalf of this entry is addressed THROUGH its value (row ->
+                // ld.global.cg of the row from L2, where the requester's red.adds were performed before its release store
+                // made the entry visible), and no mutable data is ever read through L1 here, so the L1 invalidation that an
+                // acquire at gpu scope costs (CCTL.IVALL per thread per tile) buys nothing.
+                volatile unsigned long long *p = P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1));
+                unsigned long long e = *p;
                 const long long t0 = clock64();
                 while (e == EMPTY) {
                     if (clock64() - t0 > WAIT_TIMEOUT) {
@@ -230,7 +254,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                         e = 0;
                         break;
                     }
-                    e = ld_acquire_u64(p);
+                    e = *p;
                 }
                 *p = EMPTY;
                 row_s[tid] = (uint32_t)e;
@@ -439,14 +463,19 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             bool ok = true;
             if (n_req > 0) {
                 if (lane == 0) {
-                    while ((int)(ld_acquire_u32(P.done + gwarp) - expected) < 0) {
-                        __nanosleep(32);
+                    // Poll with a plain volatile load: an acquire load inside the loop makes ptxas emit CCTL.IVALL -- an
+                    // invalidation of the SM's whole L1 -- per iteration (ncu: 2.25e9 of them per step, 16 % of all stall
+                    // samples, and every spilled register of the 24 resident warps refetched from L2).  One acquire fence
+                    // after the counter has been seen is what the protocol needs.
+                    while ((int)(ld_vol(P.done + gwarp) - expected) < 0) {
+                        __nanosleep(128);
                         if (clock64() - t1 > WAIT_TIMEOUT) {
                             *P.err = 3;
                             ok = false;
                             break;
                         }
                     }
+                    __threadfence();
                 }
                 ok = __shfl_sync(FULL, ok, 0);
                 __syncwarp();
