@@ -355,26 +355,27 @@ def timed_o2_leg(wl, steps, warmup, flush):
 
 
 def measure_l2_peak():
-    """L2-resident streaming bandwidth measured live with this library's own vectorised read-modify-write kernel
-    (comemb_scale, x *= 1 over a 32 MB buffer that stays in the 126 MB L2): read + write bytes of 40 back-to-back passes
-    between two CUDA events -- the denominator for a workload whose tables fit L2."""
+    """L2 gather/scatter peak measured live with the library's row probe (comemb_row_probe): the SGNS kernels' own access
+    mix -- coalesced 512-byte row gathers with ld.global.cg + red.global.add.v4.f32 into scattered rows, 8 rows in flight
+    per warp -- at streaming rate over a 64 MB buffer that stays in the 126 MB L2; bytes = rows gathered + rows reduced,
+    10 passes between two CUDA events, best of 3.  The denominator for a workload whose tables fit L2."""
     import torch
     from comemb_b200 import _lib
     lib = _lib.load()
-    x = torch.ones(8 << 20, dtype=torch.float32, device="cuda")
+    n_rows = (64 << 20) // 512
+    buf = torch.zeros((n_rows, 128), dtype=torch.float32, device="cuda")
+    sink = torch.zeros(1, dtype=torch.float32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    for _ in range(5):
-        _lib.check(lib.comemb_scale(x.data_ptr(), x.numel(), 1.0, st))
+    _lib.check(lib.comemb_row_probe(buf.data_ptr(), n_rows, 3, sink.data_ptr(), st))
     best = 1e9
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(40):
-            _lib.check(lib.comemb_scale(x.data_ptr(), x.numel(), 1.0, st))
+        _lib.check(lib.comemb_row_probe(buf.data_ptr(), n_rows, 10, sink.data_ptr(), st))
         e1.record()
         torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) / 40)
-    return 2 * x.numel() * 4 / (best * 1e-3) / 1e9
+        best = min(best, e0.elapsed_time(e1) / 10)
+    return 2 * n_rows * 512 / (best * 1e-3) / 1e9
 
 
 def committed_traffic(name):
@@ -485,11 +486,15 @@ def run_ours(args):
     if CFG["name"] == "sbm":
         l2_peak = measure_l2_peak()
         roofline = dict(common, bound="l2", peak=l2_peak, frac=achieved / l2_peak,
-                        peak_source="measured live: L2-resident read+write stream of comemb_scale over 32 MB (40 passes per timing, best of 3)",
+                        peak_source="measured live: comemb_row_probe (512-B row gathers + red.add.v4 scatters, the kernel's own access mix) over a 64 MB L2-resident buffer, best of 3",
                         hbm_peak=hbm_peak, frac_of_hbm_peak=achieved / hbm_peak,
+                        interface_bytes_per_pair=6208,
+                        frac_by_interface_bytes=leg["kernel_pairs_per_s_per_gpu"] * 6208 / 1e9 / l2_peak,
                         note="tables (2 x 51 MB) fit the 126 MB L2, so this workload is served by L2, not HBM (committed ncu: "
-                             "0.12x of the algorithmic bytes reach DRAM): the binding roofline is the L2 one; the HBM-bound "
-                             "regime of the same kernel is the `roofline_hbm` leg below")
+                             "0.12x of the algorithmic bytes reach DRAM): the binding roofline is the L2 one.  `achieved` "
+                             "counts the algorithmic 7168 B per pair; the kernel keeps the centre's context row in registers "
+                             "across its window, so 6208 B per pair actually cross the SM<->L2 interface "
+                             "(`frac_by_interface_bytes`).  The HBM-bound regime of the same kernel is the `roofline_hbm` leg")
     else:
         roofline = dict(common, bound="hbm", peak=hbm_peak, frac=achieved / hbm_peak, peak_source=peak_src,
                         note="tables (2 x 563 MB) exceed L2: the gather/scatter is served by HBM")

@@ -49,6 +49,7 @@ SIGNATURES = {
     "comemb_make_table": (_i32, [_vp, _i64, _f64, _vp, _i64, _vp]),
     "comemb_build_alias": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "comemb_scale": (_i32, [_vp, _i64, _f32, _vp]),
+    "comemb_row_probe": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "comemb_o2_pos_loss": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp]),
 }
 

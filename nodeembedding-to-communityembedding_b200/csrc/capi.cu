@@ -32,6 +32,7 @@ int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const floa
 int launch_transpose_blocks(const float *, float *, int, int, cudaStream_t);
 int launch_gmm_estep(const float *, int64_t, const float *, const float *, int, float *, cudaStream_t);
 int launch_scale(float *, int64_t, float, cudaStream_t);
+int launch_row_probe(float *, int64_t, int, float *, cudaStream_t);
 int launch_o2_pos_loss(const float *, const float *, int, const uint32_t *, const int64_t *, int64_t, int, double *,
                        cudaStream_t);
 int launch_walks(const int64_t *, const uint32_t *, int64_t, int, int, double, uint64_t, int, int64_t, int64_t,
@@ -351,6 +352,11 @@ int comemb_build_alias(const uint32_t *d_table, int64_t table_len, int64_t n_row
 int comemb_scale(float *d_x, int64_t n, float scale, void *stream) {
     if (!d_x || n < 0) return COMEMB_E_ARG;
     return launch_scale(d_x, n, scale, (cudaStream_t)stream);
+}
+
+int comemb_row_probe(float *d_buf, int64_t n_rows, int passes, float *d_sink, void *stream) {
+    if (!d_buf || !d_sink || n_rows < 0 || passes < 0) return COMEMB_E_ARG;
+    return launch_row_probe(d_buf, n_rows, passes, d_sink, (cudaStream_t)stream);
 }
 
 int comemb_o2_pos_loss(const float *d_node, const float *d_ctx, int size, const uint32_t *d_walks,
