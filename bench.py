@@ -449,8 +449,9 @@ def run_ours(args):
         sh = wl.sharded
         hw = torch.from_numpy(wh.view(np.int32)).pin_memory()
         hs = torch.from_numpy(seeds_h.view(np.int64)).pin_memory()
-        hn = torch.empty_like(sh.node, device="cpu").pin_memory()
-        hc = torch.empty_like(sh.ctx, device="cpu").pin_memory()
+        my_node, my_ctx = sh.node_shards[sh.rank], sh.ctx_shards[sh.rank]
+        hn = torch.empty_like(my_node, device="cpu").pin_memory()
+        hc = torch.empty_like(my_ctx, device="cpu").pin_memory()
         dw, dsd = torch.empty_like(hw, device="cuda"), torch.empty_like(hs, device="cuda")
         for s in range(1 + max(1, args.steps // 2)):
             dist.barrier()
@@ -461,12 +462,12 @@ def run_ours(args):
             sh.o2(dw, wl.off, dsd, lr, neg, W, wl.table)
             torch.cuda.synchronize()
             dist.barrier()  # the shard is complete only when every rank's remote updates have landed
-            hn.copy_(sh.node, non_blocking=True)
-            hc.copy_(sh.ctx, non_blocking=True)
+            hn.copy_(my_node, non_blocking=True)
+            hc.copy_(my_ctx, non_blocking=True)
             torch.cuda.synchronize()
             if s:
                 ms.append(time.perf_counter() - t0)
-        h2d, d2h = hw.numel() * 4 + hs.numel() * 8, 2 * sh.node.numel() * 4
+        h2d, d2h = hw.numel() * 4 + hs.numel() * 8, 2 * my_node.numel() * 4
         how = ("row-partitioned path: walks + seeds from page-locked host memory -> HBM, sharded Hogwild o2 kernel "
                "(remote rows over NVLink), barrier, this rank's row shard of both tables back to the host, every step")
     e2e_t = torch.tensor([max(ms)], dtype=torch.float64, device="cuda")

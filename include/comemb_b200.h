@@ -215,7 +215,7 @@ int comemb_scale(float *d_x, int64_t n, float scale, void *stream);
 
 /* Measurement utility (bench.py's L2 roofline denominator): the access mix of the SGNS kernels at streaming rate -- per warp
  * one coalesced 512-byte row gather (ld.global.cg) plus one red.global.add.v4.f32 of zeros into another scattered row,
- * 8 rows in flight -- over d_buf = [n_rows][128] floats, `passes` times.  d_buf is left unchanged; bytes moved per pass =
+ * 8 rows in flight -- over d_buf = [n_rows][128] floats (n_rows a power of two), `passes` times.  d_buf is left unchanged; bytes moved per pass =
  * 2 * n_rows * 512.  With a buffer that fits L2 this is the L2 gather/scatter peak. */
 int comemb_row_probe(float *d_buf, int64_t n_rows, int passes, float *d_sink, void *stream);
 

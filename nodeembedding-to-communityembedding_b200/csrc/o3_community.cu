@@ -346,8 +346,8 @@ int launch_scale(float *x, int64_t n, float s, cudaStream_t st) {
 }
 
 // Row gather/scatter probe: the access mix of the SGNS kernels at streaming rate.  Every warp walks 512-byte rows of `buf`
-// (n_rows rows) in a scrambled order: ld.global.cg of one row (lane = float4) + red.global.add.v4.f32 of zeros into another,
-// 8 rows in flight per warp.  The buffer is left unchanged.  Bytes moved per pass = 2 * n_rows * 512.
+// (n_rows rows, a power of two) in a scrambled order: ld.global.cg of one row (lane = float4) + red.global.add.v4.f32 of
+// zeros into another, 8 rows in flight per warp.  The buffer is left unchanged.  Bytes moved per pass = 2 * n_rows * 512.
 __global__ void __launch_bounds__(256) row_probe_kernel(float *buf, int64_t n_rows, int passes, float *sink) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -357,12 +357,12 @@ __global__ void __launch_bounds__(256) row_probe_kernel(float *buf, int64_t n_ro
             float4 v[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const int64_t r = ((r0 + q) * 2654435761LL + p) % n_rows;  // scattered rows, like sampled negatives
+                const int64_t r = ((r0 + q) * 2654435761LL + p) & (n_rows - 1);  // scattered rows, like sampled negatives
                 v[q] = ldcg4(buf + r * 128 + 4 * lane);
             }
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const int64_t r = ((r0 + q) * 40503LL + 7 * p + 1) % n_rows;
+                const int64_t r = ((r0 + q) * 40503LL + 7 * p + 1) & (n_rows - 1);
                 acc += v[q].x;
                 red_add4(buf + r * 128 + 4 * lane, make_float4(0.f, 0.f, 0.f, 0.f));
             }
@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(256) row_probe_kernel(float *buf, int64_t n_ro
 
 int launch_row_probe(float *buf, int64_t n_rows, int passes, float *sink, cudaStream_t st) {
     if (n_rows <= 0 || passes <= 0) return 0;
+    if (n_rows & (n_rows - 1)) return COMEMB_E_ARG;  // power of two (the row scramble is a multiply + mask)
     row_probe_kernel<<<148 * 8, 256, 0, st>>>(buf, n_rows, passes, sink);
     return (int)cudaGetLastError();
 }
