@@ -6,7 +6,7 @@
 // communities, so a warp alone can batch only ~4 rows per community (round 1 streamed 64 KB of inv_cov from L2 per such
 // group).  Here the batching is done ACROSS the ~3000 walks in flight, asynchronously:
 //
-//   one CTA per SM; 20 WALKER warps + 4 SERVICE warps per CTA.
+//   one CTA per SM; 16 WALKER warps + 8 SERVICE warps (a front and a back team of 4) per CTA.
 //   walker warp (owns a walk, one centre at a time, exactly the o2 kernel's order):
 //     [stage]  lists the rows of its next window; every row whose o3 term can be taken from the row's value at the start
 //              of the centre (all but a node that repeats inside the window) becomes a request {row, result slot} appended
@@ -16,11 +16,14 @@
 //     [sgns]   the centre's pairs (fused_sgns.cuh): SGNS on the o2 size-128 code path + the combined write with the o3
 //              term from its result slots; repeated nodes get the term in-warp from the current value, so a walk sees the
 //              reference's sequential semantics exactly.
-//   service warps of a CTA own the queues q with q % gridDim == blockIdx (community c has n_rep replicas so that every SM
-//   serves): they pop up to 64 requests, keep inv_cov_c resident in shared memory as the tcgen05 A operand (hi/lo TF32
-//   images, fetched by the TMA engine with cp.async.bulk only on a community switch), gather the rows, form x - mu_c,
-//   split hi/lo into the swizzled B operand, one thread issues 48 tcgen05.mma (3xTF32: fp32-level accuracy, accumulator in
-//   TMEM), read the accumulator back with tcgen05.ld, write w*Y to the result slots and bump the requesters' counters.
+//   service, front team: looks at all queues, takes the fullest (the resident community is favoured), claims up to 64
+//   entries with one CAS (any CTA serves any community: the load balances itself), keeps inv_cov_c resident in shared
+//   memory as the tcgen05 A operand (hi/lo TF32 images, fetched by the TMA engine with cp.async.bulk only on a community
+//   switch), gathers the rows, forms x - mu_c, splits hi/lo into the swizzled B operand, and one thread issues 48
+//   tcgen05.mma (3xTF32: fp32-level accuracy) into one of two TMEM accumulators;
+//   service, back team: waits for the tile's MMAs, reads the accumulator back with tcgen05.ld, writes Y to the result
+//   slots, release-increments the requesters' counters and hands the buffer back -- while the front team is already
+//   two steps into the next tile.
 //
 // Nothing waits on a barrier that another CTA must reach: walkers wait only for results, service warps only for
 // published entries, so the SGNS half runs at the o2 kernel's pace while the tensor half hides behind it.
@@ -38,7 +41,8 @@ constexpr int D = 128;
 constexpr int TN = 64;                      // requests per GEMM tile (tcgen05 N)
 constexpr int VMAX = 64;                    // window rows per centre (2*window <= 64)
 constexpr int A_IMG_BYTES = 2 * D * D * 4;  // hi + lo operand images of one community
-constexpr int NSVC = 4;                     // service warps (warps 0..3 of the CTA: one per TMEM lane quarter)
+constexpr int NSVC = 4;                     // warps per service team (one per TMEM lane quarter): front = warps 0..3, back = 4..7
+constexpr int ASYNC_WARPS = 24;             // warps per CTA: 8 service + 16 walkers
 constexpr int MAXQ = 64;                    // queues one CTA can own
 constexpr unsigned long long EMPTY = ~0ULL;
 constexpr long long WAIT_TIMEOUT = 8000000000LL;  // ~4 s of SM clocks: a protocol bug must end the kernel, not hang the GPU
@@ -79,19 +83,22 @@ template <int NW>
 struct AsyncSmem {
     static constexpr int A_HI = 0, A_LO = D * D * 4, B_HI = 2 * D * D * 4, B_LO = B_HI + TN * D * 4;
     static constexpr int MU = B_LO + TN * D * 4;   // float[128]
-    static constexpr int ROW = MU + D * 4;         // uint32[TN] rows of the tile
-    static constexpr int SLOT = ROW + TN * 4;      // uint32[TN] result slots
-    static constexpr int WGT = SLOT + TN * 4;      // float[TN]
-    static constexpr int LUT = WGT + TN * 4;       // float[1000]
+    static constexpr int ROW = MU + D * 4;         // uint32[2][TN] rows of the tiles in flight
+    static constexpr int SLOT = ROW + 2 * TN * 4;  // uint32[2][TN] their result slots
+    static constexpr int LUT = SLOT + 2 * TN * 4;  // float[1000]
     static constexpr int HEAD = LUT + 4096;        // uint32[MAXQ] consumed entries per owned queue
     static constexpr int WTOK = HEAD + MAXQ * 4;   // per walker warp: uint32 tok[VMAX]
     static constexpr int WINF = WTOK + NW * VMAX * 4;
     static constexpr int WX = WINF + NW * VMAX * 4;  // per walker warp: float xs[128]
     static constexpr int BAR = (WX + NW * D * 4 + 15) & ~15;
-    static constexpr int TOTAL = BAR + 64;
+    static constexpr int TOTAL = BAR + 128;
 };
 
-__device__ __forceinline__ void svc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NSVC * 32) : "memory"); }
+__device__ __forceinline__ void front_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NSVC * 32) : "memory"); }
+__device__ __forceinline__ void back_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(NSVC * 32) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ unsigned ld_vol(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
 // release / acquire at gpu scope: an entry (or a counter increment) published with release makes every write that
 // happened before it -- the publisher's own and, cumulatively, those it observed through a CTA/warp barrier -- visible to
@@ -117,13 +124,16 @@ template <bool ATOMIC, int NEG, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams P) {
     using L = AsyncSmem<NW>;
     constexpr LcgJump<NEG> J{};
-    constexpr uint32_t TMEM_COLS = 64;
+    constexpr uint32_t TMEM_COLS = 2 * TN;  // two accumulators: the back team drains one while the MMAs fill the other
     extern __shared__ char smem_raw[];
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float *lut = reinterpret_cast<float *>(smem + L::LUT);
-    uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 2);
-    int *sel = reinterpret_cast<int *>(bar_a + 3);  // service scratch: 4 ints
+    uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1, *bar_free = bar_a + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 5);
+    int *sel = reinterpret_cast<int *>(bar_a + 6);   // front scratch: 4 ints
+    int *n_s = reinterpret_cast<int *>(bar_a + 8);   // requests of the tile in buffer 0 / 1 (-1: no more tiles)
+    uint32_t *row_s = reinterpret_cast<uint32_t *>(smem + L::ROW);
+    uint32_t *slot_s = reinterpret_cast<uint32_t *>(smem + L::SLOT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
@@ -131,6 +141,9 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
     if (threadIdx.x == 0) {
         umma::mbar_init(bar_a, 1);
         umma::mbar_init(bar_mma, 1);
+        umma::mbar_init(bar_mma + 1, 1);
+        umma::mbar_init(bar_free, NSVC);
+        umma::mbar_init(bar_free + 1, NSVC);
         umma::fence_mbar_init();
     }
     umma::tc_fence_before();
@@ -140,19 +153,16 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
     const int K = P.K;
 
     if (warp < NSVC) {
-        // =============================== SERVICE WARPS ===================================================================
+        // =============================== SERVICE, FRONT TEAM (warps 0..3) ================================================
+        // claim a tile -> pop its entries -> gather rows -> B operand -> issue the MMAs into accumulator (tile & 1)
         float *mu_s = reinterpret_cast<float *>(smem + L::MU);
-        uint32_t *row_s = reinterpret_cast<uint32_t *>(smem + L::ROW);
-        uint32_t *slot_s = reinterpret_cast<uint32_t *>(smem + L::SLOT);
-        float *wgt_s = reinterpret_cast<float *>(smem + L::WGT);
-        uint32_t *head = reinterpret_cast<uint32_t *>(smem + L::HEAD);
         const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
         const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
         const int tid = threadIdx.x;  // 0..127
-        int *pick = sel;  // pick[0..2] = {queue, first ring index, count} of the claimed tile; pick[3] = scratch
-        int *wbest = reinterpret_cast<int *>(head);  // per service warp: best key of the scan
+        int *pick = sel;              // pick[0..2] = {queue, first ring index, count} of the claimed tile
+        int *wbest = reinterpret_cast<int *>(smem + L::HEAD);  // per front warp: best key of the scan
         int cur_c = -1, empty_scans = 0;
-        uint32_t par_a = 0, par_m = 0;
+        uint32_t par_a = 0;
         bool a_pending = false;
         long long tiles = 0, rows_served = 0, idle_polls = 0;
         long long ph[6] = {0, 0, 0, 0, 0, 0}, tp = clock64();
@@ -161,10 +171,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             ph[k] += now - tp;
             tp = now;
         };
-        // Pick the next tile: every service thread looks at the queues t, t+128, ...; the queue with the largest backlog
-        // wins, the resident community gets a bonus of 1.5 tiles (a switch costs a 128 KB operand fetch), and thread 0
-        // claims up to TN of its entries with one compare-and-swap (any CTA may serve any community: the load balances
-        // itself).  Result in pick[]; count 0 = nothing claimed, -1 = every walker has finished and all queues are empty.
+        // Pick the next tile: every front thread looks at the queues t, t+128, ...; the queue with the largest backlog wins,
+        // the resident community gets a bonus of 1.5 tiles (a switch costs a 128 KB operand fetch), and the thread that saw
+        // the winner claims up to TN of its entries with one compare-and-swap (any CTA may serve any community: the load
+        // balances itself).  Result in pick[]; count 0 = nothing claimed, -1 = all walkers finished and all queues empty.
         auto choose_and_claim = [&]() {
             const int live = tid == 0 ? *reinterpret_cast<volatile int *>(P.live) : 1;  // read BEFORE the queues
             int key = 0, my_backlog = 0;
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
 #pragma unroll
             for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
             if (lane == 0) wbest[warp] = best;
-            svc_barrier();
+            front_barrier();
             const int k = max(max(wbest[0], wbest[1]), max(wbest[2], wbest[3]));
             if (k > 0 && key == k) {  // the one thread that saw the winning queue claims from what it saw (no re-read)
                 const int q = k & 2047;
@@ -223,28 +233,40 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                     pick[2] = n;
                 }
             }
-            svc_barrier();
+            front_barrier();
         };
         choose_and_claim();
+        uint32_t t = 0;  // tiles issued so far; tile t uses list / accumulator buffer t & 1
         while (true) {
             const int q = pick[0], n = pick[2];
             const uint32_t base = (uint32_t)pick[1];
-            svc_barrier();  // everyone has read pick[] before it is rewritten
-            if (n < 0) break;
+            front_barrier();  // everyone has read pick[] before it is rewritten
             if (n == 0) {
                 idle_polls++;
                 __nanosleep(100);
                 choose_and_claim();
                 continue;
             }
+            const uint32_t b = t & 1u;
+            // the back team must have drained what tile t-2 left in buffer b (slot list, accumulator)
+            if (t >= 2) umma::mbar_wait(bar_free + b, ((t >> 1) - 1u) & 1u);
+            if (n < 0) {  // tell the back team to leave: an empty "tile" completes bar_mma[b] by hand
+                if (tid == 0) {
+                    n_s[b] = -1;
+                    mbar_arrive(bar_mma + b);
+                }
+                break;
+            }
             lap(0);
             const int c = q;
             const int n16 = (n + 15) & ~15;
-            if (tid < n) {  // the claimed entries are reserved, hence published within moments: take them, free the positions
+            uint32_t *row_b = row_s + b * TN, *slot_b = slot_s + b * TN;
+            if (tid < n) {
                 // Relaxed (volatile) loads: everything read on behalf of this entry is addressed THROUGH its value (row ->
                 // ld.global.cg of the row from L2, where the requester's red.adds were performed before its release store
                 // made the entry visible), and no mutable data is ever read through L1 here, so the L1 invalidation that an
-                // acquire at gpu scope costs (CCTL.IVALL per thread per tile) buys nothing.
+                // acquire at gpu scope costs (CCTL.IVALL per thread per tile) buys nothing.  The claimed entries are
+                // reserved, hence published within moments.
                 volatile unsigned long long *p = P.ring + (int64_t)q * P.cap + ((base + tid) & (uint32_t)(P.cap - 1));
                 unsigned long long e = *p;
                 const long long t0 = clock64();
@@ -257,10 +279,13 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                     e = *p;
                 }
                 *p = EMPTY;
-                row_s[tid] = (uint32_t)e;
-                slot_s[tid] = (uint32_t)(e >> 32);
+                row_b[tid] = (uint32_t)e;
+                slot_b[tid] = (uint32_t)(e >> 32);
             }
-            if (c != cur_c) {  // every MMA that read the resident A has completed (bar_mma is waited on per tile)
+            if (tid == 0) n_s[b] = n;
+            // the previous tile's MMAs have read the B operand (and A) completely before either is overwritten
+            if (t >= 1) umma::mbar_wait(bar_mma + ((t - 1u) & 1u), ((t - 1u) >> 1) & 1u);
+            if (c != cur_c) {
                 if (tid == 0) {
                     umma::mbar_expect_tx(bar_a, A_IMG_BYTES);
                     const char *src = P.a_img + (int64_t)c * A_IMG_BYTES;
@@ -273,7 +298,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 a_pending = true;
                 cur_c = c;
             }
-            svc_barrier();
+            front_barrier();
             lap(1);
             // ---- B operand: 16 rows per warp, gathers in flight 8 at a time ---------------------------------------------------
             {
@@ -284,7 +309,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
 #pragma unroll
                     for (int qq = 0; qq < 8; qq++) {
                         const int r = warp + NSVC * (half * 8 + qq);
-                        if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_s[r] * D + 4 * lane));
+                        if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_b[r] * D + 4 * lane));
                     }
 #pragma unroll
                     for (int qq = 0; qq < 8; qq++) {
@@ -304,7 +329,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 }
             }
             umma::fence_proxy_async_smem();
-            svc_barrier();
+            front_barrier();
             lap(2);
             if (warp == 0) {
                 if (a_pending) {
@@ -313,39 +338,18 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 }
                 umma::tc_fence_after();
                 if (lane == 0) {
-                    umma::issue_3xtf32(taddr, a_hi, a_lo, b_hi, b_lo, TN, n16);
-                    umma::mma_commit(bar_mma);
+                    umma::issue_3xtf32(taddr + b * (uint32_t)TN, a_hi, a_lo, b_hi, b_lo, TN, n16);
+                    umma::mma_commit(bar_mma + b);  // the back team picks the tile up from here
                 }
                 __syncwarp();
             }
             a_pending = false;
-            // the tile's slot list moves to registers: pick[] and (after the barriers inside) nothing else is reused, but
-            // the NEXT tile is chosen and claimed now, while the tensor cores work on this one
-            choose_and_claim();
-            umma::mbar_wait(bar_mma, par_m);
-            par_m ^= 1;
-            umma::tc_fence_after();
-            lap(3);
-            // ---- epilogue: service warp w reads TMEM lanes 32w..32w+31 (output coordinates), 16 requests at a time; the
-            // slot receives Y itself, the requester applies its responsibility ------------------------------------------------
-            const int a = 32 * warp + lane;
-            for (int ch = 0; ch * 16 < n16; ch++) {
-                float v[16];
-                umma::tmem_ld16(taddr + ((uint32_t)(32 * warp) << 16) + (uint32_t)(ch * 16), v);
-#pragma unroll
-                for (int qq = 0; qq < 16; qq++) {
-                    const int nn = ch * 16 + qq;
-                    if (nn < n) P.ybuf[(int64_t)slot_s[nn] * D + a] = v[qq];
-                }
-            }
-            umma::tc_fence_before();
-            svc_barrier();  // all four coordinate quarters of every result row are written ...
-            lap(4);
-            if (tid < n) red_release_add_u32(P.done + slot_s[tid] / (uint32_t)P.vslots, 1u);  // ... before the counter moves
+            t++;
             tiles++;
             rows_served += n;
-            svc_barrier();  // row_s / slot_s are free for the next tile
-            lap(5);
+            lap(3);
+            choose_and_claim();  // the next tile is claimed while the tensor cores work on this one
+            lap(4);
         }
         if (P.stats && tid == 0) {
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 0), (unsigned long long)tiles);
@@ -353,10 +357,46 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 2), (unsigned long long)idle_polls);
             for (int k = 0; k < 6; k++) atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 8 + k), (unsigned long long)ph[k]);
         }
+    } else if (warp < 2 * NSVC) {
+        // =============================== SERVICE, BACK TEAM (warps 4..7) =================================================
+        // wait for a tile's MMAs -> read the accumulator back (warp w reads TMEM lanes 32(w%4)..+31 = output coordinates) ->
+        // write Y to the requests' result slots -> release-increment the requesters' counters -> hand the buffer back
+        const int bw = warp - NSVC, btid = threadIdx.x - NSVC * 32;
+        long long t_wait = 0, t_epi = 0, tq = clock64();
+        for (uint32_t u = 0;; u++) {
+            const uint32_t b = u & 1u;
+            umma::mbar_wait(bar_mma + b, (u >> 1) & 1u);
+            umma::tc_fence_after();
+            const int n = n_s[b];
+            if (n < 0) break;
+            { const long long now = clock64(); t_wait += now - tq; tq = now; }
+            const int n16 = (n + 15) & ~15;
+            const uint32_t *slot_b = slot_s + b * TN;
+            const int a = 32 * bw + lane;
+            for (int ch = 0; ch * 16 < n16; ch++) {
+                float v[16];
+                umma::tmem_ld16(taddr + ((uint32_t)(32 * bw) << 16) + b * (uint32_t)TN + (uint32_t)(ch * 16), v);
+#pragma unroll
+                for (int qq = 0; qq < 16; qq++) {
+                    const int nn = ch * 16 + qq;
+                    if (nn < n) P.ybuf[(int64_t)slot_b[nn] * D + a] = v[qq];  // Y itself: the requester applies its responsibility
+                }
+            }
+            umma::tc_fence_before();
+            back_barrier();  // all four coordinate quarters of every result row are written ...
+            if (btid < n) red_release_add_u32(P.done + slot_b[btid] / (uint32_t)P.vslots, 1u);  // ... before the counter moves
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free + b);  // 4 arrivals: list and accumulator b are free for tile u+2
+            { const long long now = clock64(); t_epi += now - tq; tq = now; }
+        }
+        if (P.stats && btid == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 14), (unsigned long long)t_wait);
+            atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 15), (unsigned long long)t_epi);
+        }
     } else {
         // =============================== WALKER WARPS ====================================================================
-        constexpr int NWALK = NW - NSVC;
-        const int ww = warp - NSVC;
+        constexpr int NWALK = NW - 2 * NSVC;
+        const int ww = warp - 2 * NSVC;
         uint32_t *tokS = reinterpret_cast<uint32_t *>(smem + L::WTOK) + ww * VMAX;
         int32_t *infS = reinterpret_cast<int32_t *>(smem + L::WINF) + ww * VMAX;
         float *xs = reinterpret_cast<float *>(smem + L::WX) + ww * D;
@@ -508,7 +548,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
 
 template <int NEG>
 cudaError_t launch_async_t(const AsyncParams &P, bool atomic, int grid, cudaStream_t st) {
-    constexpr int NW = 24;
+    constexpr int NW = ASYNC_WARPS;
     const int smem = AsyncSmem<NW>::TOTAL + 1024;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -530,7 +570,7 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
                           uint64_t table_len, const float *mu, const float *inv_cov, int K, int window, int negative,
                           float lr, float lambda1, float lambda2, int is_node_embedding, bool atomic,
                           const int32_t *comm, const float *weight, cudaStream_t st) {
-    constexpr int NW = 24, NWALK = NW - NSVC;
+    constexpr int NW = ASYNC_WARPS, NWALK = NW - 2 * NSVC;
     if (negative < 1 || negative > 7 || window < 1 || 2 * window > VMAX || lambda2 == 0.f) return COMEMB_E_UNSUPPORTED;
     if (K < 1 || !mu || !inv_cov || !comm || !weight) return COMEMB_E_UNSUPPORTED;
     if (!is_node_embedding && negemb == node) return COMEMB_E_UNSUPPORTED;
@@ -618,8 +658,10 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
                 "cycles: stage %lld wait %lld sgns %lld (centres %lld)\n",
                 grid, n_rep, Q, h_err, h[0], h[1], h[0] ? (double)h[1] / h[0] : 0.0, h[2], h[3] / (h[6] + 1),
                 h[4] / (h[6] + 1), h[5] / (h[6] + 1), h[6]);
-        fprintf(stderr, "[async stats] service cycles per tile: probe %lld pop %lld gather %lld mma %lld epilogue %lld signal %lld\n",
-                h[8] / (h[0] + 1), h[9] / (h[0] + 1), h[10] / (h[0] + 1), h[11] / (h[0] + 1), h[12] / (h[0] + 1), h[13] / (h[0] + 1));
+        fprintf(stderr, "[async stats] front cycles per tile: wait-free %lld pop %lld gather %lld issue %lld claim-next %lld | back: "
+                "wait %lld epilogue+signal %lld\n",
+                h[8] / (h[0] + 1), h[9] / (h[0] + 1), h[10] / (h[0] + 1), h[11] / (h[0] + 1), h[12] / (h[0] + 1),
+                h[14] / (h[0] + 1), h[15] / (h[0] + 1));
     }
     cudaFreeAsync(scratch, st);
     return (int)e;
