@@ -42,8 +42,9 @@ constexpr int TN = 64;                      // requests per GEMM tile (tcgen05 N
 constexpr int VMAX = 64;                    // window rows per centre (2*window <= 64)
 constexpr int A_IMG_BYTES = 2 * D * D * 4;  // hi + lo operand images of one community
 constexpr int NSVC = 4;                     // warps per service team (one per TMEM lane quarter): front = warps 0..3, back = 4..7
-constexpr int ASYNC_WARPS = 24;             // warps per CTA: 8 service + 16 walkers
-constexpr int MAXQ = 64;                    // queues one CTA can own
+constexpr int ASYNC_WARPS = 24;             // warps per CTA: 8 service + 16 walkers (28 warps = 72 registers/thread measured slower: 5.6e8 vs 6.05e8)
+constexpr int MAXQ = 64;                    // ints of front-team scratch
+constexpr int WCTX = 2;                     // walks interleaved per walker warp
 constexpr unsigned long long EMPTY = ~0ULL;
 constexpr long long WAIT_TIMEOUT = 8000000000LL;  // ~4 s of SM clocks: a protocol bug must end the kernel, not hang the GPU
 
@@ -79,6 +80,17 @@ struct AsyncParams {
     int64_t active_warps;
 };
 
+struct WalkCtx {  // one walk in progress (shared memory; lane 0 writes, the warp reads)
+    const uint32_t *path;
+    const int32_t *rwp;
+    uint64_t rnd;       // LCG state the next pair's samples are drawn from
+    int len, ci, V;     // walk length, current centre, rows of its window
+    uint32_t wi;        // centre token
+    unsigned expected;  // requests posted so far (the completion counter must reach it)
+    int have;           // a staged centre is waiting for its sgns phase
+};
+static_assert(sizeof(WalkCtx) == 48, "layout");
+
 template <int NW>
 struct AsyncSmem {
     static constexpr int A_HI = 0, A_LO = D * D * 4, B_HI = 2 * D * D * 4, B_LO = B_HI + TN * D * 4;
@@ -87,10 +99,12 @@ struct AsyncSmem {
     static constexpr int SLOT = ROW + 2 * TN * 4;  // uint32[2][TN] their result slots
     static constexpr int LUT = SLOT + 2 * TN * 4;  // float[1000]
     static constexpr int HEAD = LUT + 4096;        // uint32[MAXQ] consumed entries per owned queue
-    static constexpr int WTOK = HEAD + MAXQ * 4;   // per walker warp: uint32 tok[VMAX]
-    static constexpr int WINF = WTOK + NW * VMAX * 4;
-    static constexpr int WX = WINF + NW * VMAX * 4;  // per walker warp: float xs[128]
-    static constexpr int BAR = (WX + NW * D * 4 + 15) & ~15;
+    static constexpr int NWALK = NW - 8;           // walker warps (8 service warps)
+    static constexpr int WTOK = HEAD + MAXQ * 4;   // per walker warp and walk context: uint32 tok[VMAX], int32 info[VMAX]
+    static constexpr int WINF = WTOK + NWALK * WCTX * VMAX * 4;
+    static constexpr int WX = WINF + NWALK * WCTX * VMAX * 4;  // per walker warp: float xs[128]
+    static constexpr int WCTXS = WX + NWALK * D * 4;            // per walker warp: WalkCtx[WCTX]
+    static constexpr int BAR = (WCTXS + NWALK * WCTX * 48 + 15) & ~15;
     static constexpr int TOTAL = BAR + 128;
 };
 
@@ -129,9 +143,11 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float *lut = reinterpret_cast<float *>(smem + L::LUT);
     uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1, *bar_free = bar_a + 3;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 5);
-    int *sel = reinterpret_cast<int *>(bar_a + 6);   // front scratch: 4 ints
-    int *n_s = reinterpret_cast<int *>(bar_a + 8);   // requests of the tile in buffer 0 / 1 (-1: no more tiles)
+    uint64_t *bar_full = bar_a + 5;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 7);
+    int *sel = reinterpret_cast<int *>(bar_a + 8);   // front scratch: 4 ints
+    int *n_s = reinterpret_cast<int *>(bar_a + 10);  // [0..1] requests of the tile in buffer 0 / 1 (-1: no more tiles),
+                                                     // [2..3] 1 if that tile waits for an operand fetch
     uint32_t *row_s = reinterpret_cast<uint32_t *>(smem + L::ROW);
     uint32_t *slot_s = reinterpret_cast<uint32_t *>(smem + L::SLOT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -144,6 +160,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         umma::mbar_init(bar_mma + 1, 1);
         umma::mbar_init(bar_free, NSVC);
         umma::mbar_init(bar_free + 1, NSVC);
+        umma::mbar_init(bar_full, 1);
+        umma::mbar_init(bar_full + 1, 1);
         umma::fence_mbar_init();
     }
     umma::tc_fence_before();
@@ -162,7 +180,6 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         int *pick = sel;              // pick[0..2] = {queue, first ring index, count} of the claimed tile
         int *wbest = reinterpret_cast<int *>(smem + L::HEAD);  // per front warp: best key of the scan
         int cur_c = -1, empty_scans = 0;
-        uint32_t par_a = 0;
         bool a_pending = false;
         long long tiles = 0, rows_served = 0, idle_polls = 0;
         long long ph[6] = {0, 0, 0, 0, 0, 0}, tp = clock64();
@@ -250,10 +267,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             const uint32_t b = t & 1u;
             // the back team must have drained what tile t-2 left in buffer b (slot list, accumulator)
             if (t >= 2) umma::mbar_wait(bar_free + b, ((t >> 1) - 1u) & 1u);
-            if (n < 0) {  // tell the back team to leave: an empty "tile" completes bar_mma[b] by hand
+            if (n < 0) {  // tell the back team to leave
                 if (tid == 0) {
                     n_s[b] = -1;
-                    mbar_arrive(bar_mma + b);
+                    mbar_arrive(bar_full + b);
                 }
                 break;
             }
@@ -285,6 +302,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             if (tid == 0) n_s[b] = n;
             // the previous tile's MMAs have read the B operand (and A) completely before either is overwritten
             if (t >= 1) umma::mbar_wait(bar_mma + ((t - 1u) & 1u), ((t - 1u) >> 1) & 1u);
+            a_pending = false;
             if (c != cur_c) {
                 if (tid == 0) {
                     umma::mbar_expect_tx(bar_a, A_IMG_BYTES);
@@ -331,17 +349,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             umma::fence_proxy_async_smem();
             front_barrier();
             lap(2);
-            if (warp == 0) {
-                if (a_pending) {
-                    umma::mbar_wait(bar_a, par_a);
-                    par_a ^= 1;
-                }
-                umma::tc_fence_after();
-                if (lane == 0) {
-                    umma::issue_3xtf32(taddr + b * (uint32_t)TN, a_hi, a_lo, b_hi, b_lo, TN, n16);
-                    umma::mma_commit(bar_mma + b);  // the back team picks the tile up from here
-                }
-                __syncwarp();
+            if (tid == 0) {  // hand the tile to the back team, which issues the MMAs (their issue blocks the issuing thread
+                             // for about the MMAs' duration: off this team's critical path)
+                n_s[2 + b] = a_pending ? 1 : 0;
+                mbar_arrive(bar_full + b);
             }
             a_pending = false;
             t++;
@@ -362,15 +373,31 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         // wait for a tile's MMAs -> read the accumulator back (warp w reads TMEM lanes 32(w%4)..+31 = output coordinates) ->
         // write Y to the requests' result slots -> release-increment the requesters' counters -> hand the buffer back
         const int bw = warp - NSVC, btid = threadIdx.x - NSVC * 32;
+        const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
+        const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
+        uint32_t par_a = 0;
         long long t_wait = 0, t_epi = 0, tq = clock64();
         for (uint32_t u = 0;; u++) {
             const uint32_t b = u & 1u;
-            umma::mbar_wait(bar_mma + b, (u >> 1) & 1u);
-            umma::tc_fence_after();
+            umma::mbar_wait(bar_full + b, (u >> 1) & 1u);  // the front team has stored the tile's B operand and lists
             const int n = n_s[b];
             if (n < 0) break;
             { const long long now = clock64(); t_wait += now - tq; tq = now; }
             const int n16 = (n + 15) & ~15;
+            if (bw == 0) {
+                if (n_s[2 + b]) {  // this tile switched the community: its operand images are still in flight
+                    umma::mbar_wait(bar_a, par_a);
+                    par_a ^= 1;
+                }
+                umma::tc_fence_after();
+                if (lane == 0) {
+                    umma::issue_3xtf32(taddr + b * (uint32_t)TN, a_hi, a_lo, b_hi, b_lo, TN, n16);
+                    umma::mma_commit(bar_mma + b);
+                }
+                __syncwarp();
+            }
+            umma::mbar_wait(bar_mma + b, (u >> 1) & 1u);
+            umma::tc_fence_after();
             const uint32_t *slot_b = slot_s + b * TN;
             const int a = 32 * bw + lane;
             for (int ch = 0; ch * 16 < n16; ch++) {
@@ -395,15 +422,18 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         }
     } else {
         // =============================== WALKER WARPS ====================================================================
+        // A warp interleaves WCTX walks: while the requests of one walk's centre are being served it runs the SGNS pairs of
+        // the other walk's centre, so the result latency (claim + gather + MMAs + epilogue, ~25K cycles) is hidden and twice
+        // as many requests are outstanding (fuller tiles).  Inside a walk everything stays sequential.
         constexpr int NWALK = NW - 2 * NSVC;
         const int ww = warp - 2 * NSVC;
-        uint32_t *tokS = reinterpret_cast<uint32_t *>(smem + L::WTOK) + ww * VMAX;
-        int32_t *infS = reinterpret_cast<int32_t *>(smem + L::WINF) + ww * VMAX;
+        uint32_t *tok_base = reinterpret_cast<uint32_t *>(smem + L::WTOK) + ww * WCTX * VMAX;
+        int32_t *inf_base = reinterpret_cast<int32_t *>(smem + L::WINF) + ww * WCTX * VMAX;
         float *xs = reinterpret_cast<float *>(smem + L::WX) + ww * D;
+        WalkCtx *cx = reinterpret_cast<WalkCtx *>(smem + L::WCTXS) + ww * WCTX;
         const int W = P.window;
         const int64_t gwarp = (int64_t)blockIdx.x * NWALK + ww;
-        const bool walker = gwarp < P.active_warps;
-        const int64_t slot0 = gwarp * P.vslots;
+        const bool walker = gwarp * WCTX < P.active_warps;  // active_warps counts walk CONTEXTS (the Hogwild concurrency cap)
         fused::SgnsArgs SA;
         SA.node = P.node; SA.ctx = P.ctx; SA.table = P.table; SA.mod = P.mod; SA.mu = P.mu; SA.inv_cov = P.inv_cov;
         SA.weight = P.weight; SA.pi = nullptr; SA.ybuf = P.ybuf; SA.K = K; SA.dense = false; SA.o3_on = true;
@@ -416,35 +446,48 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 myA = J.A[k];
                 myC = J.C[k];
             }
-        const uint32_t *path = nullptr;
-        const int32_t *rwp = nullptr;
-        int len = 0, ci = -1, V = 0;
-        uint32_t wi = 0, tnext = 0, expected = 0;
-        uint64_t rnd = 0;
-        bool exhausted = !walker;
+        bool cursor_done = !walker;  // no walk left to take
         long long t_wait = 0, t_sgns = 0, t_stage = 0, centres = 0;
-        while (!exhausted) {
-            const long long t0 = clock64();
-            // ---- [stage] the next centre with a non-empty window ---------------------------------------------------------
+        if (lane < WCTX) {
+            cx[lane].path = nullptr; cx[lane].rwp = nullptr; cx[lane].rnd = 0; cx[lane].len = 0; cx[lane].ci = -1;
+            cx[lane].V = 0; cx[lane].wi = 0; cx[lane].expected = 0; cx[lane].have = 0;
+        }
+        __syncwarp();
+
+        // ---- [stage]: advance context c to its next centre with a non-empty window and post that centre's requests -----------
+        auto stage = [&](int c) {
+            uint32_t *tokS = tok_base + c * VMAX;
+            int32_t *infS = inf_base + c * VMAX;
+            const int64_t slot0 = (gwarp * WCTX + c) * P.vslots;
+            const uint32_t *path = cx[c].path;
+            const int32_t *rwp = cx[c].rwp;
+            uint64_t rnd = cx[c].rnd;
+            int len = cx[c].len, ci = cx[c].ci, V = 0, n_req = 0;
+            uint32_t wi = 0;
             bool have = false;
-            int n_req = 0;
-            while (!exhausted) {
+            while (true) {
                 ci++;
                 if (ci >= len) {  // next walk
-                    unsigned long long w = 0;
-                    if (lane == 0) w = atomicAdd(P.walk_cursor, 1ULL);
-                    w = __shfl_sync(FULL, w, 0);
-                    if ((int64_t)w >= P.n_walks) {
-                        exhausted = true;
+                    unsigned long long w = ~0ULL;
+                    if (gwarp * WCTX + c >= P.active_warps) {  // this context is beyond the concurrency cap
+                        len = 0;
+                        break;
+                    }
+                    if (!cursor_done) {
+                        if (lane == 0) w = atomicAdd(P.walk_cursor, 1ULL);
+                        w = __shfl_sync(FULL, w, 0);
+                    }
+                    if (cursor_done || (int64_t)w >= P.n_walks) {
+                        cursor_done = true;
+                        len = 0;
                         break;
                     }
                     const int64_t o0 = __ldg(P.walk_off + w), o1 = __ldg(P.walk_off + w + 1);
                     path = P.walks + o0;
                     rwp = P.rw ? P.rw + o0 : nullptr;
                     len = (int)min((int64_t)MAX_SENTENCE_LEN, o1 - o0);
+                    // the LCG state the NEXT pair's samples are drawn from (pyx:133-134 order: lookup, then advance)
                     rnd = P.seeds ? P.seeds[w] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
-                    tnext = (lane < NEG) ? __ldg(P.table + table_slot((myA * rnd + myC) & LCG_MASK, P.mod)) : 0u;
-                    rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
                     ci = -1;
                     continue;
                 }
@@ -472,62 +515,89 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                     const uint32_t tk = mine ? tokS[vv] : 0u;
                     bool dup = false;  // an earlier window position holds the same node: o3 from the current value, in-warp
                     for (int u = 0; u < vv && mine; u++) dup = dup || (tokS[u] == tk);
-                    int c = -1;
+                    int cm = -1;
                     if (mine) {
-                        c = __ldg(P.comm + tk);
-                        if (c >= K || (c >= 0 && __ldg(P.weight + tk) == 0.f)) c = -1;
+                        cm = __ldg(P.comm + tk);
+                        if (cm >= K || (cm >= 0 && __ldg(P.weight + tk) == 0.f)) cm = -1;
                     }
-                    const int key = (mine && c >= 0 && !dup) ? c : -1 - lane;  // unique negative keys for non-requests
+                    const int key = (mine && cm >= 0 && !dup) ? cm : -1 - lane;  // unique negative keys for non-requests
                     const unsigned peers = __match_any_sync(FULL, key);
                     if (key >= 0) {
                         const int leader = __ffs(peers) - 1;
-                        const int q = c;
                         unsigned basep = 0;
-                        if (lane == leader) basep = atomicAdd(P.tail + q * 8, (unsigned)__popc(peers));
+                        if (lane == leader) basep = atomicAdd(P.tail + cm * 8, (unsigned)__popc(peers));
                         basep = __shfl_sync(peers, basep, leader);
                         const unsigned at = (basep + (unsigned)__popc(peers & ((1u << lane) - 1u))) & (unsigned)(P.cap - 1);
-                        st_release_u64(P.ring + (int64_t)q * P.cap + at,
+                        st_release_u64(P.ring + (int64_t)cm * P.cap + at,
                                        (unsigned long long)tk | ((unsigned long long)(uint32_t)(slot0 + vv) << 32));
                     }
                     n_req += __popc(__ballot_sync(FULL, key >= 0));
-                    if (mine) infS[vv] = c < 0 ? -1 : (dup ? (c | INFO_INWARP) : c);
+                    if (mine) infS[vv] = cm < 0 ? -1 : (dup ? (cm | INFO_INWARP) : cm);
                 }
-                __syncwarp();
                 have = true;
                 break;
             }
-            if (!have) break;
+            __syncwarp();
+            if (lane == 0) {
+                cx[c].path = path; cx[c].rwp = rwp; cx[c].rnd = rnd; cx[c].len = len; cx[c].ci = ci; cx[c].V = V;
+                cx[c].wi = wi; cx[c].expected += (unsigned)n_req; cx[c].have = have ? 1 : 0;
+            }
+            __syncwarp();
+        };
+
+        int remaining = 0;
+        {
+            const long long t0 = clock64();
+            for (int c = 0; c < WCTX; c++) {
+                stage(c);
+                remaining += cx[c].have;
+            }
+            t_stage += clock64() - t0;
+        }
+        for (int c = 0; remaining > 0; c = (c + 1) % WCTX) {
+            if (!cx[c].have) continue;
             const long long t1 = clock64();
             // ---- [wait] for the centre's results ----------------------------------------------------------------------------
-            expected += (unsigned)n_req;
+            const unsigned expected = cx[c].expected;
             bool ok = true;
-            if (n_req > 0) {
-                if (lane == 0) {
-                    // Poll with a plain volatile load: an acquire load inside the loop makes ptxas emit CCTL.IVALL -- an
-                    // invalidation of the SM's whole L1 -- per iteration (ncu: 2.25e9 of them per step, 16 % of all stall
-                    // samples, and every spilled register of the 24 resident warps refetched from L2).  One acquire fence
-                    // after the counter has been seen is what the protocol needs.
-                    while ((int)(ld_vol(P.done + gwarp) - expected) < 0) {
-                        __nanosleep(128);
-                        if (clock64() - t1 > WAIT_TIMEOUT) {
-                            *P.err = 3;
-                            ok = false;
-                            break;
-                        }
+            if (lane == 0) {
+                // Poll with a plain volatile load: an acquire load inside the loop makes ptxas emit CCTL.IVALL -- an
+                // invalidation of the SM's whole L1 -- per iteration (ncu: 2.25e9 of them per step, 16 % of all stall samples,
+                // and every spilled register of the resident warps refetched from L2).  One acquire fence after the counter
+                // has been seen is what the protocol needs.
+                while ((int)(ld_vol(P.done + gwarp * WCTX + c) - expected) < 0) {
+                    __nanosleep(64);
+                    if (clock64() - t1 > WAIT_TIMEOUT) {
+                        *P.err = 3;
+                        ok = false;
+                        break;
                     }
-                    __threadfence();
                 }
-                ok = __shfl_sync(FULL, ok, 0);
-                __syncwarp();
+                __threadfence();
             }
+            ok = __shfl_sync(FULL, ok, 0);
+            __syncwarp();
             if (!ok) break;
             const long long t2 = clock64();
             // ---- [sgns] -----------------------------------------------------------------------------------------------------
-            fused::sgns_centre<ATOMIC, NEG>(SA, wi, V, tokS, infS, xs, lut, slot0, rnd, tnext, myA, myC, lane);
+            {
+                const uint64_t r0 = cx[c].rnd;
+                const int V = cx[c].V;
+                uint32_t tnext = (lane < NEG) ? __ldg(P.table + table_slot((myA * r0 + myC) & LCG_MASK, P.mod)) : 0u;
+                uint64_t radv = (J.A[NEG] * r0 + J.C[NEG]) & LCG_MASK;
+                fused::sgns_centre<ATOMIC, NEG>(SA, cx[c].wi, V, tok_base + c * VMAX, inf_base + c * VMAX, xs, lut,
+                                                (gwarp * WCTX + c) * P.vslots, radv, tnext, myA, myC, lane);
+                __syncwarp();
+                if (lane == 0) cx[c].rnd = lcg_skip(r0, (uint64_t)V * (uint64_t)NEG);  // V pairs consumed NEG draws each
+                __syncwarp();
+            }
             const long long t3 = clock64();
-            t_stage += t1 - t0;
+            stage(c);
+            if (!cx[c].have) remaining--;
+            const long long t4 = clock64();
             t_wait += t2 - t1;
             t_sgns += t3 - t2;
+            t_stage += t4 - t3;
             centres++;
         }
         __syncwarp();
@@ -580,13 +650,13 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop) return COMEMB_E_UNSUPPORTED;
-    int64_t warps = (int64_t)sms * NWALK;
+    int64_t warps = (int64_t)sms * NWALK * WCTX;  // walks in flight (walk contexts)
     if (comemb_opts().max_warps > 0 && comemb_opts().max_warps < warps) warps = comemb_opts().max_warps;
     if (n_walks < warps) warps = n_walks;
-    const int grid = (int)((warps + NWALK - 1) / NWALK);
+    const int grid = (int)((warps + NWALK * WCTX - 1) / (NWALK * WCTX));
     const int n_rep = 1, Q = K;  // one queue per community, served by whichever CTAs find it the fullest
     if (Q > 2047) return COMEMB_E_UNSUPPORTED;
-    const int64_t total_warps = (int64_t)grid * NWALK;
+    const int64_t total_warps = (int64_t)grid * NWALK * WCTX;  // walk contexts: each has its result slots and counter
     const int vslots = 2 * window;
     // a walker has at most vslots requests in flight, so total_warps * vslots bounds the entries of one queue that are
     // reserved and not yet popped; twice that keeps a ring position's reuse far away from the pop that freed it
@@ -611,7 +681,7 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     cudaError_t e = cudaMemsetAsync(scratch + o_ctl, 0, sz_ctl, st);
     if (e != cudaSuccess) return fail(e);
     if ((e = cudaMemsetAsync(scratch + o_ring, 0xFF, (size_t)Q * cap * 8, st)) != cudaSuccess) return fail(e);
-    const int h_live = (int)warps;
+    const int h_live = (int)((warps + WCTX - 1) / WCTX);  // walker warps with at least one active context
     if ((e = cudaMemcpyAsync(scratch + o_ctl + 48, &h_live, 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
     const int r = launch_umma_prep_a(inv_cov, scratch + o_img, K, st);
     if (r) return fail((cudaError_t)r);
