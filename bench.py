@@ -670,6 +670,32 @@ def run_secondary_block(wl, flush):
                  "kernel": "o3_gemm_kernel (bucket rows by community + tcgen05 3xTF32 tiles)", "bound": "tensor/L2",
                  "tflops_3xtf32": v * 3 * 2 * d * d / 1e12, "hbm_gbs": v * 2 * d * 4 / 1e9,
                  "frac_of_hbm_peak": v * 2 * d * 4 / 1e9 / peak}
+    # BASELINE configs[2] shape (BlogCatalog: 10 312 nodes / 334K edges, conf.ini: window 5, 3 negatives): a table of 10K rows
+    # is where Hogwild staleness bites, so the learners cap the walks in flight at max(workers, n_rows/28) (368 here);
+    # throughput with that cap and with the whole GPU (3552 warps on 10K rows)
+    try:
+        from comemb_b200.utils import graph_utils as gu
+        nb, Lb, Wb, negb = 10312, 80, 5, 3
+        Gb = gu.powerlaw_graph(nb, 333983, seed=7)
+        degb = np.ascontiguousarray(np.diff(Gb.rowptr), np.float64)
+        tabb = torch.empty(2000000, dtype=torch.int32, device="cuda")
+        _lib.check(wl.lib.comemb_make_table(degb.ctypes.data, degb.size, 0.75, tabb.data_ptr(), tabb.numel(), None))
+        nwb = 5 * nb
+        wb, lb = gu.build_deepwalk_corpus(Gb, 5, Lb, alpha=0.0, seed=3, mode=gu.MODE_HOGWILD, return_device=True)
+        offb = torch.arange(nwb + 1, dtype=torch.int64, device="cuda") * Lb
+        nh, ch = init_tables_host(nb, d, seed=2)
+        nodeb, ctxb = torch.from_numpy(nh).cuda(), torch.from_numpy(ch).cuda()
+        pairs_b = pairs_of_len(Lb, Wb) * nwb
+        res = {}
+        for tag, cap in (("capped_n_rows_over_28", K.hogwild_concurrency(nb, 1)), ("uncapped", 0)):
+            ms = _timed(lambda: K.o2_batch(nodeb, ctxb, wb.reshape(-1), offb, None, cfg["lr"], negb, Wb, tabb,
+                                           mode=K.MODE_HOGWILD, flags=K.F_ATOMIC, base_seed=9, max_warps=cap), 1, 2, flush)
+            res[tag] = {"value": pairs_b / (ms * 1e-3), "ms_per_launch": ms, "max_warps": cap or "all (3552)"}
+        out["o2_config3_shape"] = {"metric": METRIC, "unit": UNIT, "pairs_per_launch": pairs_b,
+                                   "workload": "power-law graph 10 312 nodes / 334K edges, 5 walks per node, L=80, window 5, 3 negatives",
+                                   **res}
+    except Exception as e:
+        out["o2_config3_shape"] = {"error": repr(e)}
     # walker alone
     nw = 10 * n
     L = cfg["L"]

@@ -42,7 +42,10 @@ constexpr int TN = 64;                      // requests per GEMM tile (tcgen05 N
 constexpr int VMAX = 64;                    // window rows per centre (2*window <= 64)
 constexpr int A_IMG_BYTES = 2 * D * D * 4;  // hi + lo operand images of one community
 constexpr int NSVC = 4;                     // warps per service team (one per TMEM lane quarter): front = warps 0..3, back = 4..7
-constexpr int ASYNC_WARPS = 24;             // warps per CTA: 8 service + 16 walkers (28 warps = 72 registers/thread measured slower: 5.6e8 vs 6.05e8)
+constexpr int ASYNC_WARPS = 28;             // warps per CTA: 8 service + 20 walkers.  896 threads leave 72 registers per thread at
+                                            // launch; the service warpgroups give registers back (setmaxnreg.dec -> 48) and the
+                                            // walker warpgroups take them (setmaxnreg.inc -> 80), like the 24-warp build
+constexpr int SVC_REGS = 48, WALK_REGS = 80;
 constexpr int MAXQ = 64;                    // ints of front-team scratch
 constexpr int WCTX = 2;                     // walks interleaved per walker warp
 constexpr unsigned long long EMPTY = ~0ULL;
@@ -102,12 +105,15 @@ struct AsyncSmem {
     static constexpr int NWALK = NW - 8;           // walker warps (8 service warps)
     static constexpr int WTOK = HEAD + MAXQ * 4;   // per walker warp and walk context: uint32 tok[VMAX], int32 info[VMAX]
     static constexpr int WINF = WTOK + NWALK * WCTX * VMAX * 4;
-    static constexpr int WX = WINF + NWALK * WCTX * VMAX * 4;  // per walker warp: float xs[128]
-    static constexpr int WCTXS = WX + NWALK * D * 4;            // per walker warp: WalkCtx[WCTX]
+    static constexpr int WCTXS = WINF + NWALK * WCTX * VMAX * 4;  // per walker warp: WalkCtx[WCTX]
     static constexpr int BAR = (WCTXS + NWALK * WCTX * 48 + 15) & ~15;
     static constexpr int TOTAL = BAR + 128;
 };
 
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void front_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NSVC * 32) : "memory"); }
 __device__ __forceinline__ void back_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(NSVC * 32) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -172,7 +178,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
 
     if (warp < NSVC) {
         // =============================== SERVICE, FRONT TEAM (warps 0..3) ================================================
-        // claim a tile -> pop its entries -> gather rows -> B operand -> issue the MMAs into accumulator (tile & 1)
+        // claim a tile -> pop its entries -> gather rows -> B operand -> hand it to the back team
+        if (NW * 32 > 768) reg_dec<SVC_REGS>();
         float *mu_s = reinterpret_cast<float *>(smem + L::MU);
         const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
         const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
@@ -318,20 +325,21 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
             front_barrier();
             lap(1);
-            // ---- B operand: 16 rows per warp, gathers in flight 8 at a time ---------------------------------------------------
+            // ---- B operand: 16 rows per warp, gathers in flight GB at a time ---------------------------------------------------
             {
+                constexpr int GB = NW * 32 > 768 ? 4 : 8;  // fewer in flight when the team runs on 48 registers
                 const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    float4 xv[8];
+                for (int half = 0; half < 16 / GB; half++) {
+                    float4 xv[GB];
 #pragma unroll
-                    for (int qq = 0; qq < 8; qq++) {
-                        const int r = warp + NSVC * (half * 8 + qq);
+                    for (int qq = 0; qq < GB; qq++) {
+                        const int r = warp + NSVC * (half * GB + qq);
                         if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_b[r] * D + 4 * lane));
                     }
 #pragma unroll
-                    for (int qq = 0; qq < 8; qq++) {
-                        const int r = warp + NSVC * (half * 8 + qq);
+                    for (int qq = 0; qq < GB; qq++) {
+                        const int r = warp + NSVC * (half * GB + qq);
                         if (r < n) {
                             const float4 x = xv[qq];
                             const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
@@ -372,6 +380,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         // =============================== SERVICE, BACK TEAM (warps 4..7) =================================================
         // wait for a tile's MMAs -> read the accumulator back (warp w reads TMEM lanes 32(w%4)..+31 = output coordinates) ->
         // write Y to the requests' result slots -> release-increment the requesters' counters -> hand the buffer back
+        if (NW * 32 > 768) reg_dec<SVC_REGS>();
         const int bw = warp - NSVC, btid = threadIdx.x - NSVC * 32;
         const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
         const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
@@ -425,11 +434,11 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         // A warp interleaves WCTX walks: while the requests of one walk's centre are being served it runs the SGNS pairs of
         // the other walk's centre, so the result latency (claim + gather + MMAs + epilogue, ~25K cycles) is hidden and twice
         // as many requests are outstanding (fuller tiles).  Inside a walk everything stays sequential.
+        if (NW * 32 > 768) reg_inc<WALK_REGS>();
         constexpr int NWALK = NW - 2 * NSVC;
         const int ww = warp - 2 * NSVC;
         uint32_t *tok_base = reinterpret_cast<uint32_t *>(smem + L::WTOK) + ww * WCTX * VMAX;
         int32_t *inf_base = reinterpret_cast<int32_t *>(smem + L::WINF) + ww * WCTX * VMAX;
-        float *xs = reinterpret_cast<float *>(smem + L::WX) + ww * D;
         WalkCtx *cx = reinterpret_cast<WalkCtx *>(smem + L::WCTXS) + ww * WCTX;
         const int W = P.window;
         const int64_t gwarp = (int64_t)blockIdx.x * NWALK + ww;
@@ -585,7 +594,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 const int V = cx[c].V;
                 uint32_t tnext = (lane < NEG) ? __ldg(P.table + table_slot((myA * r0 + myC) & LCG_MASK, P.mod)) : 0u;
                 uint64_t radv = (J.A[NEG] * r0 + J.C[NEG]) & LCG_MASK;
-                fused::sgns_centre<ATOMIC, NEG>(SA, cx[c].wi, V, tok_base + c * VMAX, inf_base + c * VMAX, xs, lut,
+                fused::sgns_centre<ATOMIC, NEG>(SA, cx[c].wi, V, tok_base + c * VMAX, inf_base + c * VMAX, lut,
                                                 (gwarp * WCTX + c) * P.vslots, radv, tnext, myA, myC, lane);
                 __syncwarp();
                 if (lane == 0) cx[c].rnd = lcg_skip(r0, (uint64_t)V * (uint64_t)NEG);  // V pairs consumed NEG draws each

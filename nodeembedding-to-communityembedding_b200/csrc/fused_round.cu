@@ -90,8 +90,7 @@ struct RoundSmem {
     static constexpr int SCAN = LUT + 4096;               // int[KMAX + 1] exclusive tile prefix
     static constexpr int WTOK = SCAN + (KMAX + 1) * 4 + 12;  // per warp: uint32 tok[VMAX]
     static constexpr int WINF = WTOK + NW * VMAX * 4;     // per warp: int32 info[VMAX] (community or -1, bit 30 = in-warp o3)
-    static constexpr int WX = WINF + NW * VMAX * 4;       // per warp: float xs[128] (in-warp o3 staging)
-    static constexpr int BAR = (WX + NW * D * 4 + 15) & ~15;
+    static constexpr int BAR = (WINF + NW * VMAX * 4 + 15) & ~15;
     static constexpr int TOTAL = BAR + 64;
 };
 
@@ -146,7 +145,6 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *tokS = reinterpret_cast<uint32_t *>(smem + L::WTOK) + warp * VMAX;
     int32_t *infS = reinterpret_cast<int32_t *>(smem + L::WINF) + warp * VMAX;
-    float *xs = reinterpret_cast<float *>(smem + L::WX) + warp * D;
 
     for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
     if (warp == 0) umma::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -446,7 +444,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_round_kernel(const RoundParams 
         lap(2);
         // ---- [sgns] of the staged centre, then stage the next one -------------------------------------------------------------
         if (have)
-            fused::sgns_centre<ATOMIC, NEG>(SA, wi, V, tokS, infS, xs, lut, slot0, rnd, tnext, myA, myC, lane);
+            fused::sgns_centre<ATOMIC, NEG>(SA, wi, V, tokS, infS, lut, slot0, rnd, tnext, myA, myC, lane);
         par ^= 1;
         lap(3);
         stage_next(par);

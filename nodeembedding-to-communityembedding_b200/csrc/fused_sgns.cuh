@@ -32,11 +32,11 @@ struct SgnsArgs {
 
 __device__ __forceinline__ float clipf(float v, float c) { return fminf(fmaxf(v, -c), c); }
 
-// tokS/infS: this warp's window rows and their info words; xs: 128 floats of per-warp staging; lut: sigma table (shared).
+// tokS/infS: this warp's window rows and their info words; lut: sigma table (shared).
 // rnd/tnext: the walk's LCG state and the prefetched samples of the next pair (advanced here).
 template <bool ATOMIC, int NEG>
 __device__ __forceinline__ void sgns_centre(const SgnsArgs &P, const uint32_t wi, const int V, const uint32_t *tokS,
-                                            const int32_t *infS, float *xs, const float *lut, const int64_t slot0,
+                                            const int32_t *infS, const float *lut, const int64_t slot0,
                                             uint64_t &rnd, uint32_t &tnext, const uint64_t myA, const uint64_t myC,
                                             const int lane) {
     constexpr LcgJump<NEG> J{};
@@ -73,18 +73,19 @@ __device__ __forceinline__ void sgns_centre(const SgnsArgs &P, const uint32_t wi
                     const float p = dense ? __ldg(P.pi + (int64_t)wj * K + k) : __ldg(P.weight + wj);
                     if (p == 0.f) continue;
                     const float4 mk = __ldg(reinterpret_cast<const float4 *>(P.mu + (int64_t)k * D + 4 * lane));
-                    __syncwarp();
-                    *reinterpret_cast<float4 *>(xs + 4 * lane) =
-                        make_float4(r1.x - mk.x, r1.y - mk.y, r1.z - mk.z, r1.w - mk.w);
-                    __syncwarp();
+                    const float4 dv = make_float4(r1.x - mk.x, r1.y - mk.y, r1.z - mk.z, r1.w - mk.w);  // diff[4*lane .. +3]
                     const float4 *S = reinterpret_cast<const float4 *>(P.inv_cov + (int64_t)k * D * D) + lane;
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-                    for (int b = 0; b < D; b++) {  // column-major read: operand element (a,b) = S[b*128 + a]
-                        const float4 s = __ldg(S + b * 32);
-                        const float d = xs[b];
-                        t.x = fmaf(s.x, d, t.x); t.y = fmaf(s.y, d, t.y);
-                        t.z = fmaf(s.z, d, t.z); t.w = fmaf(s.w, d, t.w);
+#pragma unroll 2
+                    for (int b4 = 0; b4 < 32; b4++) {  // column-major read: operand element (a,b) = S[b*128 + a]; b ascending
+                        const float4 s0 = __ldg(S + (4 * b4 + 0) * 32), s1 = __ldg(S + (4 * b4 + 1) * 32);
+                        const float4 s2 = __ldg(S + (4 * b4 + 2) * 32), s3 = __ldg(S + (4 * b4 + 3) * 32);
+                        const float d0 = __shfl_sync(FULL, dv.x, b4), d1 = __shfl_sync(FULL, dv.y, b4);
+                        const float d2 = __shfl_sync(FULL, dv.z, b4), d3 = __shfl_sync(FULL, dv.w, b4);
+                        t.x = fmaf(s0.x, d0, t.x); t.y = fmaf(s0.y, d0, t.y); t.z = fmaf(s0.z, d0, t.z); t.w = fmaf(s0.w, d0, t.w);
+                        t.x = fmaf(s1.x, d1, t.x); t.y = fmaf(s1.y, d1, t.y); t.z = fmaf(s1.z, d1, t.z); t.w = fmaf(s1.w, d1, t.w);
+                        t.x = fmaf(s2.x, d2, t.x); t.y = fmaf(s2.y, d2, t.y); t.z = fmaf(s2.z, d2, t.z); t.w = fmaf(s2.w, d2, t.w);
+                        t.x = fmaf(s3.x, d3, t.x); t.y = fmaf(s3.y, d3, t.y); t.z = fmaf(s3.z, d3, t.z); t.w = fmaf(s3.w, d3, t.w);
                     }
                     y.x = fmaf(p, t.x, y.x); y.y = fmaf(p, t.y, y.y);
                     y.z = fmaf(p, t.z, y.z); y.w = fmaf(p, t.w, y.w);
