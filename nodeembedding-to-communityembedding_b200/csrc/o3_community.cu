@@ -18,6 +18,8 @@
 
 int launch_o3_gemm(float *, const uint32_t *, int64_t, const float *, const float *, const int32_t *, const float *, int,
                    float, float, int, cudaStream_t);
+int launch_o3_gemm_sparse(float *, const uint32_t *, int64_t, const float *, const float *, const float *, int, float, float,
+                          int, cudaStream_t);
 
 namespace {
 
@@ -279,6 +281,12 @@ int launch_o3_batch(float *node, int64_t n_rows, int size, const uint32_t *rows,
         // one on ill-conditioned covariances (karate: 34 points in 128 dimensions give |inv_cov| ~ 1e5, where any two
         // fp32 summation orders -- the reference's BLAS included -- differ by more than 1e-5 of the row).
         const int r = launch_o3_gemm(node, rows, n_sel, mu, inv_cov_t, comm, weight, K, scale, lr, iters, st);
+        if (r != COMEMB_E_UNSUPPORTED) return r;
+    }
+    if (pi && size == 128 && (variant == COMEMB_VARIANT_TENSOR || (variant == COMEMB_VARIANT_DEFAULT && n_sel >= 1024))) {
+        // dense pi pointer: when its rows are sparse (<= 8 non-zero responsibilities per row on average) the same grouped
+        // GEMM runs with one entry per (row, community) and red.add accumulation; a truly dense pi stays below
+        const int r = launch_o3_gemm_sparse(node, rows, n_sel, mu, inv_cov_t, pi, K, scale, lr, iters, st);
         if (r != COMEMB_E_UNSUPPORTED) return r;
     }
     if (!pi && size == 128 && variant != COMEMB_VARIANT_GENERIC && n_sel >= 4 * O3F_T && n_sel < (1LL << 31) && K < (1 << 30)) {

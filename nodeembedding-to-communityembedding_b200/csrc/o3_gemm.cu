@@ -5,13 +5,17 @@
 //   up to TN rows of it).  A persistent CTA per SM walks a contiguous range of jobs; for each it
 //     * keeps inv_cov_c resident in shared memory as the tcgen05 A operand (hi/lo TF32 images, 128 KB, fetched by
 //       the TMA engine with cp.async.bulk only when the community changes),
-//     * gathers the rows, forms diff = x - mu_c, splits it into hi/lo TF32 and stores the swizzled B operand,
+//     * gathers the rows (prefetched into registers while the previous tile is in the tensor cores, then kept in shared
+//       memory across the `iters` iterations), forms diff = x - mu_c, splits it into hi/lo TF32 and stores the swizzled B
+//       operand,
 //     * one elected thread issues 48 tcgen05.mma (3xTF32, see umma.cuh) with the accumulator in TMEM,
 //     * all warps read the accumulator back (tcgen05.ld) and apply  x -= clip(w * G * (beta/K), +-5) * lr.
 //
 // Accuracy: 3xTF32 products with fp32 accumulation -- the same fp32-level result as the reference's numpy matmul up to
 // summation order (tests: <= 1e-5 against the reference's golden output; the previous CUDA-core kernel mirrored the
 // ORACLE's double-accumulated dot bit for bit, which the reference itself does not do).
+#include <vector>
+
 #include "comemb_common.cuh"
 #include "umma.cuh"
 
@@ -96,6 +100,9 @@ __global__ void o3g_scatter_kernel(const uint32_t *rows, int64_t n_sel, const in
 // ---- the grouped GEMM ------------------------------------------------------------------------------------------------------------
 struct O3GemmParams {
     float *node;
+    float *gbuf;            // ACCUM mode: [n_sel][128] gradient accumulators (red.add), indexed by selection slot
+    const uint32_t *sslot;  // ACCUM mode: selection slot of every bucketed entry
+    const float *sw;        // ACCUM mode: responsibility of every bucketed entry
     const uint32_t *srows;
     const int4 *jobs;
     const int *n_jobs;
@@ -113,7 +120,10 @@ struct O3GemmSmem {
     static constexpr int TOTAL = BAR + 32;
 };
 
-template <int TN, int WARPS>
+// ACCUM = false: top-1 pi, the epilogue applies the update.  ACCUM = true: sparse pi with several non-zero responsibilities
+// per row -- one bucketed entry per (row, community), the epilogue adds w * G into the row's accumulator (red.add; a
+// second kernel applies the clipped update), one pass per launch.
+template <int TN, int WARPS, bool ACCUM>
 __global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmParams P) {
     using L = O3GemmSmem<TN>;
     static_assert(TN % 16 == 0 && TN <= 256 && WARPS % 4 == 0, "tile shape");
@@ -142,12 +152,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmPara
 
     const int n_jobs = *P.n_jobs;
     const int j0 = (int)((int64_t)n_jobs * blockIdx.x / gridDim.x), j1 = (int)((int64_t)n_jobs * (blockIdx.x + 1) / gridDim.x);
+    float *x_s = reinterpret_cast<float *>(smem + ((L::TOTAL + 15) & ~15));  // [TN][128] the tile's rows (fp32) for the epilogue
     int cur_c = -1;
     uint32_t par_a = 0, par_m = 0;
     bool a_pending = false;
+    constexpr int RPW = (TN + WARPS - 1) / WARPS;  // rows per warp
+    uint32_t rowv[RPW];
+    float4 xv[RPW];
+    float wv[RPW];
+    // rows of job j into registers: all gathers in flight at once, issued while the previous tile is still in the tensor cores
+    auto prefetch = [&](int j) {
+        const int4 job = __ldg(P.jobs + j);
+#pragma unroll
+        for (int q = 0; q < RPW; q++) {
+            const int r = warp + q * WARPS;
+            rowv[q] = r < job.z ? __ldg(P.srows + job.y + r) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < RPW; q++) {
+            const int r = warp + q * WARPS;
+            if (r < job.z) {
+                xv[q] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)rowv[q] * D + 4 * lane));
+                wv[q] = ACCUM ? __ldg(P.sw + job.y + r) : __ldg(P.weight + rowv[q]);
+                if (ACCUM) rowv[q] = __ldg(P.sslot + job.y + r);  // from here on the "row" is the accumulator slot
+            }
+        }
+    };
+    if (j0 < j1) prefetch(j0);
     for (int j = j0; j < j1; j++) {
-        const int4 job = P.jobs[j];
-        const int c = job.x, start = job.y, cnt = job.z;
+        const int4 job = __ldg(P.jobs + j);
+        const int c = job.x, cnt = job.z;
         const int n16 = (cnt + 15) & ~15;
         if (c != cur_c) {  // every MMA that read the resident A has completed (bar_mma was waited on below)
             if (threadIdx.x == 0) {
@@ -162,27 +196,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmPara
             cur_c = c;
             __syncthreads();  // mu_s visible
         }
-        for (int it = 0; it < P.iters; it++) {
+        const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
+        // the tile's rows: registers -> shared memory (kept there across the iterations: nothing is re-read from global)
+#pragma unroll
+        for (int q = 0; q < RPW; q++) {
+            const int r = warp + q * WARPS;
+            if (r < cnt) {
+                *reinterpret_cast<float4 *>(x_s + r * D + 4 * lane) = xv[q];
+                if (lane == 0) {
+                    row_s[r] = rowv[q];
+                    wgt_s[r] = wv[q];
+                }
+            }
+        }
+        const int iters = ACCUM ? 1 : P.iters;
+        for (int it = 0; it < iters; it++) {
+            __syncthreads();  // x_s of this iteration is complete
             // ---- B operand: diff rows, hi/lo split, swizzled K-major ----------------------------------------------------
-            const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
-            constexpr int RPW = (TN + WARPS - 1) / WARPS;  // rows per warp: all gathers in flight before the first use
-            uint32_t rowv[RPW];
-            float4 xv[RPW];
-#pragma unroll
-            for (int q = 0; q < RPW; q++) {
-                const int r = warp + q * WARPS;
-                rowv[q] = r < cnt ? __ldg(P.srows + start + r) : 0u;
-            }
-#pragma unroll
-            for (int q = 0; q < RPW; q++) {
-                const int r = warp + q * WARPS;
-                if (r < cnt) xv[q] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)rowv[q] * D + 4 * lane));
-            }
 #pragma unroll
             for (int q = 0; q < RPW; q++) {
                 const int r = warp + q * WARPS;
                 if (r < cnt) {
-                    const float4 x = xv[q];
+                    const float4 x = *reinterpret_cast<const float4 *>(x_s + r * D + 4 * lane);
                     const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
                     const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y), umma::tf32_round(df.z),
                                                   umma::tf32_round(df.w));
@@ -191,10 +226,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmPara
                     const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
                     *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
                     *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
-                    if (it == 0 && lane == 0) {
-                        row_s[r] = rowv[q];
-                        wgt_s[r] = __ldg(P.weight + rowv[q]);
-                    }
                 }
             }
             umma::fence_proxy_async_smem();
@@ -212,33 +243,34 @@ __global__ void __launch_bounds__(WARPS * 32, 1) o3_gemm_kernel(const O3GemmPara
                 __syncwarp();
             }
             a_pending = false;
+            if (it == iters - 1 && j + 1 < j1) prefetch(j + 1);  // the next tile's rows travel while the tensor cores work
             umma::mbar_wait(bar_mma, par_m);
             par_m ^= 1;
             umma::tc_fence_after();
             // ---- epilogue: thread = output coordinate a of TMEM lane quarter (warp % 4), 16 rows at a time ----------------
             const int a = 32 * (warp & 3) + lane;
             for (int ch = warp >> 2; ch * 16 < n16; ch += WARPS / 4) {
-                float v[16], xo[16];
+                float v[16];
                 umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ch * 16), v);
-#pragma unroll
-                for (int q = 0; q < 16; q++) {  // the 16 old values first: independent loads, one latency
-                    const int n = ch * 16 + q;
-                    xo[q] = n < cnt ? __ldcg(P.node + (int64_t)row_s[n] * D + a) : 0.f;
-                }
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const int n = ch * 16 + q;
                     if (n < cnt) {
-                        float g = __fmul_rn(__fmul_rn(wgt_s[n], v[q]), P.scale);  // :71, :76
-                        g = fminf(fmaxf(g, -5.f), 5.f);                           // :77
-                        P.node[(int64_t)row_s[n] * D + a] = xo[q] - __fmul_rn(g, P.lr);
+                        if (ACCUM) {
+                            atomicAdd(P.gbuf + (int64_t)row_s[n] * D + a, __fmul_rn(wgt_s[n], v[q]));  // :71-72 summed over k
+                        } else {
+                            float g = __fmul_rn(__fmul_rn(wgt_s[n], v[q]), P.scale);  // :71, :76
+                            g = fminf(fmaxf(g, -5.f), 5.f);                           // :77
+                            const float nx = x_s[n * D + a] - __fmul_rn(g, P.lr);
+                            x_s[n * D + a] = nx;
+                            if (it == iters - 1) P.node[(int64_t)row_s[n] * D + a] = nx;
+                        }
                     }
                 }
             }
             umma::tc_fence_before();
-            __threadfence();
-            __syncthreads();  // accumulator and B images are free again; the updated rows are visible to the CTA
         }
+        __syncthreads();  // accumulator, operand images and x_s are free for the next tile
     }
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(taddr, TMEM_COLS);
@@ -291,13 +323,136 @@ int launch_o3_gemm(float *node, const uint32_t *rows, int64_t n_sel, const float
     O3GemmParams P;
     P.node = node; P.srows = srows; P.jobs = jobs; P.n_jobs = n_jobs; P.mu = mu; P.a_img = img; P.weight = weight;
     P.scale = scale; P.lr = lr; P.iters = iters;
-    const int smem = L::TOTAL + 1024;
-    e = cudaFuncSetAttribute(o3_gemm_kernel<TN, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = L::TOTAL + 1024 + 16 + TN * D * 4;  // + the tile's rows in fp32
+    P.gbuf = nullptr; P.sslot = nullptr; P.sw = nullptr;
+    e = cudaFuncSetAttribute(o3_gemm_kernel<TN, WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(e);
     const int grid = (int)(max_jobs < sms ? max_jobs : sms);
-    o3_gemm_kernel<TN, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
+    o3_gemm_kernel<TN, WARPS, false><<<grid, WARPS * 32, smem, st>>>(P);
     e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
+    return (int)e;
+}
+
+// ---- sparse pi (several non-zero responsibilities per row): entries (row, community, weight) bucketed by community ---------------
+namespace {
+__global__ void o3s_count_kernel(const uint32_t *rows, int64_t n_sel, const float *pi, int K, int *count) {
+    // one warp per selected row: lanes scan the row's K responsibilities (coalesced)
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = w0; s < n_sel; s += nw) {
+        const int64_t r = rows ? rows[s] : s;
+        for (int k = lane; k < K; k += 32)
+            if (pi[r * K + k] != 0.f) atomicAdd(count + k, 1);
+    }
+}
+__global__ void o3s_scatter_kernel(const uint32_t *rows, int64_t n_sel, const float *pi, int K, int *cursor, uint32_t *srows,
+                                   uint32_t *sslot, float *sw) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = w0; s < n_sel; s += nw) {
+        const int64_t r = rows ? rows[s] : s;
+        for (int k = lane; k < K; k += 32) {
+            const float p = pi[r * K + k];
+            if (p != 0.f) {
+                const int at = atomicAdd(cursor + k, 1);
+                srows[at] = (uint32_t)r;
+                sslot[at] = (uint32_t)s;
+                sw[at] = p;
+            }
+        }
+    }
+}
+// x_r -= clip(G_s * scale, +-5) * lr  (community_embeddings.py:76-77), and the accumulator is cleared for the next iteration
+__global__ void o3s_apply_kernel(float *node, const uint32_t *rows, int64_t n_sel, float *gbuf, float scale, float lr) {
+    const int64_t n4 = n_sel * (D / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = i / (D / 4);
+        const int q = (int)(i % (D / 4));
+        const int64_t r = rows ? rows[s] : s;
+        float4 g = *reinterpret_cast<float4 *>(gbuf + s * D + 4 * q);
+        *reinterpret_cast<float4 *>(gbuf + s * D + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 *xp = reinterpret_cast<float4 *>(node + r * D + 4 * q);
+        float4 x = *xp;
+        x.x -= __fmul_rn(fminf(fmaxf(__fmul_rn(g.x, scale), -5.f), 5.f), lr);
+        x.y -= __fmul_rn(fminf(fmaxf(__fmul_rn(g.y, scale), -5.f), 5.f), lr);
+        x.z -= __fmul_rn(fminf(fmaxf(__fmul_rn(g.z, scale), -5.f), 5.f), lr);
+        x.w -= __fmul_rn(fminf(fmaxf(__fmul_rn(g.w, scale), -5.f), 5.f), lr);
+        *xp = x;
+    }
+}
+}  // namespace
+
+// dense pi pointer whose rows are SPARSE (at most max_nnz_per_row non-zeros on average): size 128.  Returns
+// COMEMB_E_UNSUPPORTED when pi is too dense to pay off (the caller keeps the one-row-per-warp kernel).
+int launch_o3_gemm_sparse(float *node, const uint32_t *rows, int64_t n_sel, const float *mu, const float *inv_cov_t,
+                          const float *pi, int K, float scale, float lr, int iters, cudaStream_t st) {
+    constexpr int TN = 64, WARPS = 16;
+    using L = O3GemmSmem<TN>;
+    if (n_sel <= 0 || iters <= 0) return 0;
+    if (n_sel >= (1LL << 28) || K > (1 << 20)) return COMEMB_E_UNSUPPORTED;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // pass 1: entries per community (the host needs the total to size the entry arrays: one small synchronous copy)
+    int *count = nullptr;
+    CUDA_TRY(cudaMallocAsync(&count, (size_t)(2 * K + 4) * 4, st));
+    auto fail0 = [&](cudaError_t e) {
+        cudaFreeAsync(count, st);
+        return (int)e;
+    };
+    cudaError_t e = cudaMemsetAsync(count, 0, (size_t)K * 4, st);
+    if (e != cudaSuccess) return fail0(e);
+    const int gw = (int)((n_sel + 7) / 8 < sms * 8 ? (n_sel + 7) / 8 : sms * 8);
+    o3s_count_kernel<<<gw, 256, 0, st>>>(rows, n_sel, pi, K, count);
+    std::vector<int> h_count(K);
+    if ((e = cudaMemcpyAsync(h_count.data(), count, (size_t)K * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail0(e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail0(e);
+    int64_t nnz = 0;
+    for (int k = 0; k < K; k++) nnz += h_count[k];
+    if (nnz > 8 * n_sel || nnz >= (1LL << 31)) return fail0((cudaError_t)0), COMEMB_E_UNSUPPORTED;
+    if (nnz == 0) return fail0((cudaError_t)0), 0;
+    const int64_t max_jobs = (nnz + TN - 1) / TN + K;
+    char *scratch = nullptr;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        const size_t at = off;
+        off = (off + bytes + 1023) & ~(size_t)1023;
+        return at;
+    };
+    const size_t o_jobs = carve((size_t)max_jobs * 16), o_rows = carve((size_t)nnz * 4), o_slot = carve((size_t)nnz * 4);
+    const size_t o_w = carve((size_t)nnz * 4), o_g = carve((size_t)n_sel * D * 4), o_img = carve((size_t)K * A_IMG_BYTES);
+    if ((e = cudaMallocAsync(&scratch, off, st)) != cudaSuccess) return fail0(e);
+    auto fail = [&](cudaError_t err) {
+        cudaFreeAsync(scratch, st);
+        cudaFreeAsync(count, st);
+        return (int)err;
+    };
+    int *cursor = count + K, *n_jobs = count + 2 * K;
+    int4 *jobs = reinterpret_cast<int4 *>(scratch + o_jobs);
+    uint32_t *srows = reinterpret_cast<uint32_t *>(scratch + o_rows), *sslot = reinterpret_cast<uint32_t *>(scratch + o_slot);
+    float *sw = reinterpret_cast<float *>(scratch + o_w), *gbuf = reinterpret_cast<float *>(scratch + o_g);
+    o3g_scan_kernel<TN><<<1, 1024, 0, st>>>(count, K, cursor, jobs, n_jobs);
+    o3s_scatter_kernel<<<gw, 256, 0, st>>>(rows, n_sel, pi, K, cursor, srows, sslot, sw);
+    if ((e = cudaMemsetAsync(gbuf, 0, (size_t)n_sel * D * 4, st)) != cudaSuccess) return fail(e);
+    int r = launch_umma_prep_a(inv_cov_t, scratch + o_img, K, st);
+    if (r) return fail((cudaError_t)r);
+    O3GemmParams P;
+    P.node = node; P.gbuf = gbuf; P.sslot = sslot; P.sw = sw; P.srows = srows; P.jobs = jobs; P.n_jobs = n_jobs; P.mu = mu;
+    P.a_img = scratch + o_img; P.weight = nullptr; P.scale = scale; P.lr = lr; P.iters = 1;
+    const int smem = L::TOTAL + 1024 + 16 + TN * D * 4;
+    if ((e = cudaFuncSetAttribute(o3_gemm_kernel<TN, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        return fail(e);
+    const int grid = (int)(max_jobs < sms ? max_jobs : sms);
+    const int64_t n4 = n_sel * (D / 4);
+    for (int it = 0; it < iters; it++) {  // the gradient is frozen per iteration (:64-73), applied once (:76-77)
+        o3_gemm_kernel<TN, WARPS, true><<<grid, WARPS * 32, smem, st>>>(P);
+        o3s_apply_kernel<<<(int)((n4 + 255) / 256 < sms * 8 ? (n4 + 255) / 256 : sms * 8), 256, 0, st>>>(node, rows, n_sel, gbuf,
+                                                                                                         scale, lr);
+    }
+    e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    cudaFreeAsync(count, st);
     return (int)e;
 }
 

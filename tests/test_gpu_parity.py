@@ -1432,3 +1432,35 @@ def test_config3_shape_fused_pass_fast_vs_generic(K):
         qa = np.quantile(np.linalg.norm(out["fast"], axis=1), [0.5, 0.9, 0.99])
         qb = np.quantile(np.linalg.norm(out["generic"], axis=1), [0.5, 0.9, 0.99])
         assert np.all(np.abs(qa - qb) <= 0.05 * qb) and corr > 0.5, (dense, qa, qb, corr)
+
+
+@pytest.mark.parametrize("iters", [1, 2])
+def test_o3_sparse_pi_through_the_tensor_core_path(K, iters):
+    """Community2Vec.train's update for a pi whose rows hold 1-3 non-zero responsibilities (what predict_proba gives near
+    community borders): one bucketed entry per (row, community), tcgen05 3xTF32 tiles, red.add accumulation of w * G per
+    row, clipped update applied once per iteration (o3_gemm.cu, ACCUM mode) -- against the oracle's dense evaluation:
+    <= 1e-5 of the table scale and <= 2e-5 of the update; rows outside the selection untouched."""
+    rs = np.random.RandomState(31)
+    N, d, Kc = 5000, 128, 9
+    node = (rs.uniform(-1, 1, (N, d)) * 0.3).astype(np.float32)
+    mu = rs.uniform(-0.5, 0.5, (Kc, d)).astype(np.float32)
+    inv = (rs.normal(size=(Kc, d, d)) * 0.05 + np.eye(d)).astype(np.float32)
+    pi = np.zeros((N, Kc), np.float32)
+    for _ in range(3):
+        hit = rs.rand(N) < (1.0 if _ == 0 else 0.4)
+        pi[np.flatnonzero(hit), rs.randint(0, Kc, int(hit.sum()))] += rs.uniform(0.1, 1.0, int(hit.sum())).astype(np.float32)
+    pi[::23] = 0.0
+    pi /= np.maximum(pi.sum(1, keepdims=True), 1e-9)
+    pi = pi.astype(np.float32)
+    assert ((pi != 0).sum(1) > 1).mean() > 0.3
+    rows = rs.permutation(N)[: N - 300].astype(np.uint32)
+    dn = dev(node)
+    K.o3_batch(dn, dev(rows), dev(mu), K.transpose_blocks(dev(inv)), dev(pi), 3.0, 0.05, iters=iters)
+    got = host(dn)
+    want = node.copy()
+    O.o3_batch(want, rows, mu, inv, pi, 3.0, 0.05, iters)
+    assert np.abs(want - node).max() > 1e-3
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), np.abs(got - want).max()
+    assert np.abs((got - node) - (want - node)).max() <= 2e-5 * np.abs(want - node).max() + 6e-8
+    untouched = np.setdiff1d(np.arange(N), rows)
+    assert np.array_equal(got[untouched], node[untouched])
