@@ -696,6 +696,23 @@ def run_secondary_block(wl, flush):
                                    **res}
     except Exception as e:
         out["o2_config3_shape"] = {"error": repr(e)}
+    # o2 at the other specialised sizes (64: half-warp rows, 256: two float4 per lane) on the same walks: pairs/s and the
+    # algorithmic bytes/s (4*size*14 per pair) next to the size-128 figure
+    try:
+        wl.step(4242)
+        res = {}
+        for dsz in (64, 256):
+            nh, ch = init_tables_host(n, dsz, seed=3)
+            nd, cd = torch.from_numpy(nh).cuda(), torch.from_numpy(ch).cuda()
+            ms = _timed(lambda: K.o2_batch(nd, cd, wl.walks.reshape(-1), wl.off, None, cfg["lr"], neg, cfg["W"], wl.table,
+                                           mode=K.MODE_HOGWILD, flags=K.F_ATOMIC, base_seed=5), 1, 2, flush)
+            v = wl.pairs_of_current_walks() / (ms * 1e-3)
+            res["size_%d" % dsz] = {"value": v, "unit": UNIT, "ms_per_launch": ms, "algorithmic_bytes_per_pair": 4 * dsz * 14,
+                                    "achieved_gbs": v * 4 * dsz * 14 / 1e9, "kernel": "o2_hogwild_dx_kernel"}
+            del nd, cd
+        out["o2_other_sizes"] = res
+    except Exception as e:
+        out["o2_other_sizes"] = {"error": repr(e)}
     # walker alone
     nw = 10 * n
     L = cfg["L"]

@@ -508,6 +508,210 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
     }
 }
 
+// ---- o2, sizes 64 and 256: the size-128 instruction stream with another row width ---------------------------------------------
+// NV float4 per lane: size 256 = lane l owns elements 4l..4l+3 and 128+4l..128+4l+3 (the layout of the any-size kernel and
+// of the oracle's warp-order model, so a single warp stays bit-exact); HALF: size 64 = lanes 0..15 own 4l..4l+3, the
+// upper half-warp carries zeros (it still takes part in the shuffles and draws samples).  Everything else as
+// o2_hogwild_d128_kernel: compile-time NEG, LCG jump constants, samples one pair ahead, transposed reduction,
+// lane-parallel sigma, duplicate samples on the sequential path.  (The any-size kernel spends ~650 warp-instructions per
+// pair on run-time loops; this one ~330 x NV.)
+template <int NV>
+struct RowV {
+    float4 v[NV];
+};
+
+template <bool ATOMIC, int NEG, int NV, bool HALF>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogwild_dx_kernel(const O2Params P) {
+    static_assert(NEG >= 1 && NEG <= 7 && (NV == 1 || NV == 2) && !(HALF && NV != 1), "shape");
+    constexpr int D = HALF ? 64 : 128 * NV;
+    constexpr LcgJump<NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const bool act = !HALF || lane < 16;  // this lane owns part of a row
+    const int W = P.window;
+    const float lr = P.lr, lambda = P.lambda;
+    float *const node_l = P.node + 4 * lane, *const ctx_l = P.ctx + 4 * lane;
+    const Draw draw = P.draw;
+    auto LD = [&](const float *p) {
+        RowV<NV> r;
+#pragma unroll
+        for (int m = 0; m < NV; m++) r.v[m] = act ? ldcg4(p + 128 * m) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return r;
+    };
+    auto ST = [&](float *p, const RowV<NV> &r) {
+#pragma unroll
+        for (int m = 0; m < NV; m++)
+            if (act) st4(p + 128 * m, r.v[m]);
+    };
+    auto RED = [&](float *p, const RowV<NV> &r) {
+#pragma unroll
+        for (int m = 0; m < NV; m++)
+            if (act) red_add4(p + 128 * m, r.v[m]);
+    };
+    auto DOT = [&](const RowV<NV> &a, const RowV<NV> &b) {  // the any-size kernel's order: element index ascending
+        float acc = 0.f;
+#pragma unroll
+        for (int m = 0; m < NV; m++) {
+            acc = fmaf(a.v[m].x, b.v[m].x, acc);
+            acc = fmaf(a.v[m].y, b.v[m].y, acc);
+            acc = fmaf(a.v[m].z, b.v[m].z, acc);
+            acc = fmaf(a.v[m].w, b.v[m].w, acc);
+        }
+        return acc;
+    };
+    auto FMA = [&](RowV<NV> &y, float g, const RowV<NV> &x) {  // y += g * x
+#pragma unroll
+        for (int m = 0; m < NV; m++) {
+            y.v[m].x = fmaf(g, x.v[m].x, y.v[m].x); y.v[m].y = fmaf(g, x.v[m].y, y.v[m].y);
+            y.v[m].z = fmaf(g, x.v[m].z, y.v[m].z); y.v[m].w = fmaf(g, x.v[m].w, y.v[m].w);
+        }
+    };
+    auto MUL = [&](float g, const RowV<NV> &x) {
+        RowV<NV> r;
+#pragma unroll
+        for (int m = 0; m < NV; m++)
+            r.v[m] = make_float4(__fmul_rn(g, x.v[m].x), __fmul_rn(g, x.v[m].y), __fmul_rn(g, x.v[m].z), __fmul_rn(g, x.v[m].w));
+        return r;
+    };
+    auto ZERO = [&]() {
+        RowV<NV> r;
+#pragma unroll
+        for (int m = 0; m < NV; m++) r.v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return r;
+    };
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    const int pi = ((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1);
+    const float my_label = pi == 0 ? 1.f : 0.f;
+    const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+
+    for (int64_t w = warp0; w < P.n_walks; w += n_warps) {
+        const uint32_t *path = P.walks + P.walk_off[w];
+        const int len = (int)min((int64_t)MAX_SENTENCE_LEN, P.walk_off[w + 1] - P.walk_off[w]);  // pyx:480
+        uint64_t rnd = P.seeds ? P.seeds[w] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)w)) & LCG_MASK);
+        if (P.n_tokens) {  // train_o2's return value (pyx:490)
+            int cnt = 0;
+            for (int i = lane; i < len; i += 32) cnt += (__ldg(path + i) != COMEMB_TOKEN_NONE);
+            cnt = __reduce_add_sync(FULL, cnt);
+            if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(P.n_tokens), (unsigned long long)cnt);
+        }
+        uint32_t tnext = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
+        rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+        for (int i = 0; i < len; i++) {  // pyx:494
+            const uint32_t wi = __ldg(path + i);
+            if (wi == COMEMB_TOKEN_NONE) continue;
+            float *pos_ptr = ctx_l + (int64_t)wi * D;
+            RowV<NV> cpos = LD(pos_ptr), dpos = ZERO();
+            const int j1 = min(len, i + W + 1);
+            for (int j = max(0, i - W); j < j1; j++) {  // pyx:503
+                const uint32_t wj = __ldg(path + j);
+                if (j == i || wj == COMEMB_TOKEN_NONE) continue;
+                float *row1_ptr = node_l + (int64_t)wj * D;
+                const RowV<NV> r1 = LD(row1_ptr);
+                const uint32_t tmine = tnext;
+                tnext = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
+                rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
+                uint32_t t[NEG];
+#pragma unroll
+                for (int k = 0; k < NEG; k++) t[k] = __shfl_sync(FULL, tmine, k);
+                bool anydup = false;
+#pragma unroll
+                for (int k = 1; k < NEG; k++)
+#pragma unroll
+                    for (int a = 0; a < k; a++) anydup = anydup || (t[a] == t[k]);
+                RowV<NV> work = ZERO();
+                if (!anydup) {
+                    RowV<NV> c[NEG];
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) c[k] = LD(ctx_l + (int64_t)t[k] * D);
+                    float p[8];
+                    p[0] = DOT(r1, cpos);
+#pragma unroll
+                    for (int k = 0; k < 7; k++) p[k + 1] = k < NEG ? DOT(r1, c[k < NEG ? k : 0]) : 0.f;
+                    const float fm = reduce8_transposed(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], lane);
+                    bool live = pi == 0;
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) live = live || (pi == k + 1 && t[k] != wi);
+                    float gm = 0.f;
+                    if (live && fm > -MAX_EXP_F && fm < MAX_EXP_F)  // pyx:141-144
+                        gm = __fmul_rn(__fmul_rn(my_label - lut[lut_index(fm)], lr), lambda);
+                    {
+                        const float g = __shfl_sync(FULL, gm, lane_of_p(0));
+                        FMA(work, g, cpos);  // pyx:146
+                        if (ATOMIC) FMA(dpos, g, r1);
+                        FMA(cpos, g, r1);  // pyx:147 (registers)
+                    }
+#pragma unroll
+                    for (int k = 0; k < NEG; k++) {
+                        const float g = __shfl_sync(FULL, gm, lane_of_p(k + 1));
+                        FMA(work, g, c[k]);  // pyx:146
+                        if (g != 0.f) {
+                            float *cp = ctx_l + (int64_t)t[k] * D;
+                            if (ATOMIC) {
+                                RED(cp, MUL(g, r1));
+                            } else {  // pyx:147
+                                RowV<NV> nc = c[k];
+                                FMA(nc, g, r1);
+                                ST(cp, nc);
+                            }
+                        }
+                    }
+                } else {  // equal samples inside one pair: target by target, re-reading rows
+                    {
+                        const float f = warp_sum_xor(DOT(r1, cpos));
+                        if (f > -MAX_EXP_F && f < MAX_EXP_F) {
+                            const float g = sgns_g(f, 1.f, lr, lambda, lut);
+                            FMA(work, g, cpos);
+                            if (ATOMIC) FMA(dpos, g, r1);
+                            FMA(cpos, g, r1);
+                        }
+                    }
+#pragma unroll 1
+                    for (int k = 0; k < NEG; k++) {
+                        const uint32_t tk = __shfl_sync(FULL, tmine, k);
+                        if (tk == wi) continue;  // pyx:135-136
+                        float *cp = ctx_l + (int64_t)tk * D;
+                        const RowV<NV> c = LD(cp);
+                        const float f = warp_sum_xor(DOT(r1, c));
+                        if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;  // pyx:141-142
+                        const float g = sgns_g(f, 0.f, lr, lambda, lut);
+                        FMA(work, g, c);
+                        if (ATOMIC) {
+                            RED(cp, MUL(g, r1));
+                        } else {
+                            RowV<NV> nc = c;
+                            FMA(nc, g, r1);
+                            ST(cp, nc);
+                        }
+                    }
+                }
+                if (ATOMIC) {  // pyx:149
+                    RED(row1_ptr, work);
+                } else {
+                    RowV<NV> nr;
+#pragma unroll
+                    for (int m = 0; m < NV; m++)
+                        nr.v[m] = make_float4(r1.v[m].x + work.v[m].x, r1.v[m].y + work.v[m].y, r1.v[m].z + work.v[m].z,
+                                              r1.v[m].w + work.v[m].w);
+                    ST(row1_ptr, nr);
+                }
+            }
+            if (ATOMIC)
+                RED(pos_ptr, dpos);
+            else
+                ST(pos_ptr, cpos);
+        }
+    }
+}
+
 // ---- o1 -------------------------------------------------------------------------------------------------------------------
 struct O1Params {
     float *node;
@@ -759,6 +963,31 @@ int launch_o2_d128(const O2Params &P, bool atomic, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+template <int NEG, int NV, bool HALF>
+int launch_o2_dx(const O2Params &P, bool atomic, cudaStream_t st) {
+    if (atomic) {
+        auto k = o2_hogwild_dx_kernel<true, NEG, NV, HALF>;
+        k<<<grid_for(k, P.n_walks), WARPS_PER_BLOCK * 32, 0, st>>>(P);
+    } else {
+        auto k = o2_hogwild_dx_kernel<false, NEG, NV, HALF>;
+        k<<<grid_for(k, P.n_walks), WARPS_PER_BLOCK * 32, 0, st>>>(P);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <int NV, bool HALF>
+int launch_o2_dx_neg(const O2Params &P, int negative, bool atomic, cudaStream_t st) {
+    switch (negative) {
+        case 1: return launch_o2_dx<1, NV, HALF>(P, atomic, st);
+        case 2: return launch_o2_dx<2, NV, HALF>(P, atomic, st);
+        case 3: return launch_o2_dx<3, NV, HALF>(P, atomic, st);
+        case 4: return launch_o2_dx<4, NV, HALF>(P, atomic, st);
+        case 5: return launch_o2_dx<5, NV, HALF>(P, atomic, st);
+        case 6: return launch_o2_dx<6, NV, HALF>(P, atomic, st);
+        default: return launch_o2_dx<7, NV, HALF>(P, atomic, st);
+    }
+}
+
 template <int NCH, bool VEC>
 int launch_o1_t(const O1Params &P, bool atomic, cudaStream_t st) {
     if (atomic) {
@@ -806,6 +1035,10 @@ int launch_o2_hogwild(float *node, float *ctx, int size, const uint32_t *walks, 
             default: break;
         }
     }
+    // sizes 64 and 256: the specialised instruction stream (no alias sampler / centre-chunked units there)
+    if ((size == 64 || size == 256) && negative >= 1 && negative <= 7 && comemb_opts().variant != COMEMB_VARIANT_GENERIC &&
+        P.units_per_walk == 1 && (reinterpret_cast<uintptr_t>(node) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0)
+        return size == 64 ? launch_o2_dx_neg<1, true>(P, negative, atomic, st) : launch_o2_dx_neg<2, false>(P, negative, atomic, st);
     if (size <= 128) return vec ? launch_o2_t<1, true>(P, atomic, st) : launch_o2_t<1, false>(P, atomic, st);
     if (size <= 256) return vec ? launch_o2_t<2, true>(P, atomic, st) : launch_o2_t<2, false>(P, atomic, st);
     return vec ? launch_o2_t<4, true>(P, atomic, st) : launch_o2_t<4, false>(P, atomic, st);
