@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) o2_hogwild_d128_ke
 
 // ---- o2, sizes 64 and 256: the size-128 instruction stream with another row width ---------------------------------------------
 // NV float4 per lane: size 256 = lane l owns elements 4l..4l+3 and 128+4l..128+4l+3 (the layout of the any-size kernel and
-// of the oracle's warp-order model, so a single warp stays bit-exact); HALF: size 64 = lanes 0..15 own 4l..4l+3, the
-// upper half-warp carries zeros (it still takes part in the shuffles and draws samples).  Everything else as
+// of the oracle's warp-order model, so a single warp stays bit-exact); HALF: size 64 = lane l owns elements 2l, 2l+1 (one
+// 64-bit access per lane, 256 contiguous bytes per row; the oracle models this order as DOT_WARP2).  Everything else as
 // o2_hogwild_d128_kernel: compile-time NEG, LCG jump constants, samples one pair ahead, transposed reduction,
 // lane-parallel sigma, duplicate samples on the sequential path.  (The any-size kernel spends ~650 warp-instructions per
 // pair on run-time loops; this one ~330 x NV.)
@@ -529,26 +529,37 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogw
     for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const bool act = !HALF || lane < 16;  // this lane owns part of a row
     const int W = P.window;
     const float lr = P.lr, lambda = P.lambda;
-    float *const node_l = P.node + 4 * lane, *const ctx_l = P.ctx + 4 * lane;
+    float *const node_l = P.node + (HALF ? 2 : 4) * lane, *const ctx_l = P.ctx + (HALF ? 2 : 4) * lane;
     const Draw draw = P.draw;
+    // HALF: the lane's two elements travel in .x/.y, .z/.w stay +0 (fma(0, 0, acc) == acc: the sums are untouched)
     auto LD = [&](const float *p) {
         RowV<NV> r;
+        if (HALF) {
+            const float2 t = __ldcg(reinterpret_cast<const float2 *>(p));
+            r.v[0] = make_float4(t.x, t.y, 0.f, 0.f);
+        } else {
 #pragma unroll
-        for (int m = 0; m < NV; m++) r.v[m] = act ? ldcg4(p + 128 * m) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int m = 0; m < NV; m++) r.v[m] = ldcg4(p + 128 * m);
+        }
         return r;
     };
     auto ST = [&](float *p, const RowV<NV> &r) {
+        if (HALF) {
+            *reinterpret_cast<float2 *>(p) = make_float2(r.v[0].x, r.v[0].y);
+        } else {
 #pragma unroll
-        for (int m = 0; m < NV; m++)
-            if (act) st4(p + 128 * m, r.v[m]);
+            for (int m = 0; m < NV; m++) st4(p + 128 * m, r.v[m]);
+        }
     };
     auto RED = [&](float *p, const RowV<NV> &r) {
+        if (HALF) {
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(r.v[0].x), "f"(r.v[0].y) : "memory");
+        } else {
 #pragma unroll
-        for (int m = 0; m < NV; m++)
-            if (act) red_add4(p + 128 * m, r.v[m]);
+            for (int m = 0; m < NV; m++) red_add4(p + 128 * m, r.v[m]);
+        }
     };
     auto DOT = [&](const RowV<NV> &a, const RowV<NV> &b) {  // the any-size kernel's order: element index ascending
         float acc = 0.f;

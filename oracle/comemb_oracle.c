@@ -28,7 +28,8 @@
 enum {
     ORACLE_DOT_REFBLAS_QUIRK = 0, /* FAST_VERSION 0 on the golden machine: SkylakeX sdot read back as a double */
     ORACLE_DOT_REFBLAS = 1,       /* FAST_VERSION 1: same sdot, plain float return (pyx:190) */
-    ORACLE_DOT_WARP = 2           /* summation order of the CUDA Hogwild kernels (lane-strided fma + xor butterfly) */
+    ORACLE_DOT_WARP = 2,          /* summation order of the CUDA Hogwild kernels (lane-strided fma + xor butterfly) */
+    ORACLE_DOT_WARP2 = 3          /* same, size-64 specialisation: lane l owns elements 2l, 2l+1 */
 };
 
 static float EXP_TABLE[EXP_TABLE_SIZE];
@@ -91,15 +92,16 @@ static float sdot_skx(const float *x, const float *y, int n, int quirk) {
     return (float)seen;
 }
 
-/* Summation order of the CUDA Hogwild kernels: lane l (0..31) owns elements 128m+4l..128m+4l+3, fma-accumulates
- * them in increasing order starting from +0, then an xor-butterfly (16,8,4,2,1) adds across lanes. */
-static float sdot_warp(const float *x, const float *y, int n) {
+/* Summation order of the CUDA Hogwild kernels: lane l (0..31) owns elements 128m+4l..128m+4l+3 (per_lane = 4; the size-64
+ * specialisation: 2l, 2l+1, per_lane = 2), fma-accumulates them in increasing order starting from +0, then an
+ * xor-butterfly (16,8,4,2,1) adds across lanes. */
+static float sdot_warp(const float *x, const float *y, int n, int per_lane) {
     float v[32], w[32];
     for (int l = 0; l < 32; l++) {
         float acc = 0.0f;
-        for (int base = 0; base < n; base += 128)
-            for (int c = 0; c < 4; c++) {
-                int e = base + 4 * l + c;
+        for (int base = 0; base < n; base += 32 * per_lane)
+            for (int c = 0; c < per_lane; c++) {
+                int e = base + per_lane * l + c;
                 if (e < n) acc = fmaf(x[e], y[e], acc);
             }
         v[l] = acc;
@@ -112,7 +114,8 @@ static float sdot_warp(const float *x, const float *y, int n) {
 }
 
 float oracle_dot(const float *x, const float *y, int n, int model) {
-    if (model == ORACLE_DOT_WARP) return sdot_warp(x, y, n);
+    if (model == ORACLE_DOT_WARP) return sdot_warp(x, y, n, 4);
+    if (model == ORACLE_DOT_WARP2) return sdot_warp(x, y, n, 2);
     return sdot_skx(x, y, n, model == ORACLE_DOT_REFBLAS_QUIRK);
 }
 

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libcomemb_oracle.so")
 DOT_REFBLAS_QUIRK = 0  # reference as built in the authoring container (FAST_VERSION 0, OpenBLAS SkylakeX sdot)
 DOT_REFBLAS = 1        # FAST_VERSION 1 flavour
 DOT_WARP = 2           # summation order of the CUDA Hogwild kernels
+DOT_WARP2 = 3          # ... of the size-64 specialisation (lane l owns elements 2l, 2l+1)
 TOKEN_NONE = 0xFFFFFFFF
 
 _lib = None

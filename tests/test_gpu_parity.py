@@ -379,11 +379,12 @@ def test_o2_hogwild_generic_kernel_at_d128(K, name):
 
 
 @pytest.mark.parametrize("variant", [0, 900])
-@pytest.mark.parametrize("neg,d", [(1, 128), (2, 128), (6, 128), (7, 128), (12, 64), (8, 128), (3, 128), (4, 128)])
+@pytest.mark.parametrize("neg,d", [(1, 128), (2, 128), (6, 128), (7, 128), (12, 64), (8, 128), (3, 128), (4, 128), (1, 64),
+                                   (5, 64), (7, 64), (1, 256), (5, 256), (7, 256), (9, 256)])
 def test_o2_hogwild_other_negative_counts(K, neg, d, variant):
-    """negative = 1..7 at size 128 take the specialised kernel (compile-time NEG); everything else -- and variant 9 --
-    the generic kernel, which gathers negatives in batches of 5 (7, 8 and 12: several batches).  Single warp vs the
-    oracle, bit for bit."""
+    """negative = 1..7 at sizes 64 / 128 / 256 take the specialised kernels (compile-time NEG; size 64: two elements per
+    lane, size 256: two float4 per lane); everything else -- and variant 9 -- the generic kernel, which gathers negatives
+    in batches of 5 (7, 8, 9 and 12: several batches).  Single warp vs the oracle, bit for bit."""
     from comemb_b200 import _lib
     c = dict(cases.O2_CASES["o2_d128_small"], neg=neg, d=d, seed=900 + neg)
     _lib.check(_lib.load().comemb_set_tuning(0, 0, variant))
@@ -407,7 +408,10 @@ def _o2_single_warp(K, name, atomic):
         K.o2_batch(dn, dc, dev(w), dev(off), dev(np.array([s], np.uint64)), c["lr"], c["neg"], c["W"], dt,
                    alpha=c["lam"], mode=K.MODE_HOGWILD, flags=K.F_ATOMIC if atomic else 0)
     flat, off = cases.flatten_walks(walks)
-    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], c["neg"], c["W"], table, c["lam"], O.DOT_WARP)
+    # the size-64 specialisation (1..7 negatives, not the any-size kernel) gives every lane two elements instead of four
+    from comemb_b200 import _lib as _l
+    d64 = c["d"] == 64 and 1 <= c["neg"] <= 7 and _l.get_opts().variant != _l.VARIANT_GENERIC
+    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], c["neg"], c["W"], table, c["lam"], O.DOT_WARP2 if d64 else O.DOT_WARP)
     if atomic:
         # red.add adds round(g*x) to the row in L2, the sequential oracle fuses the product (fma): one rounding more per
         # update, which now and then moves a later dot across a sigma-LUT bucket edge (1/83 wide).  Measured over the golden
