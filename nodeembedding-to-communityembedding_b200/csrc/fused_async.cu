@@ -140,6 +140,39 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Rows r = first, first + 8, first + 16, ... (< n) of the tile: gather from the node table, subtract mu_c, split hi/lo TF32 and
+// store into the swizzled B operand images.  Each service team takes every other group of four rows (front: first = warp,
+// back: first = 4 + warp), GB rows in flight per warp.
+template <int GB>
+__device__ __forceinline__ void gather_rows(const AsyncParams &P, char *b_hi_img, char *b_lo_img, const uint32_t *row_b,
+                                            const float *mu_s, int first, int n, int lane) {
+    const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
+#pragma unroll
+    for (int half = 0; half < 8 / GB; half++) {
+        float4 xv[GB];
+#pragma unroll
+        for (int qq = 0; qq < GB; qq++) {
+            const int r = first + 8 * (half * GB + qq);
+            if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_b[r] * D + 4 * lane));
+        }
+#pragma unroll
+        for (int qq = 0; qq < GB; qq++) {
+            const int r = first + 8 * (half * GB + qq);
+            if (r < n) {
+                const float4 x = xv[qq];
+                const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+                const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y), umma::tf32_round(df.z),
+                                              umma::tf32_round(df.w));
+                const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
+                                              umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
+                const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
+                *reinterpret_cast<float4 *>(b_hi_img + off) = hi;
+                *reinterpret_cast<float4 *>(b_lo_img + off) = lo;
+            }
+        }
+    }
+}
+
 template <bool ATOMIC, int NEG, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams P) {
     using L = AsyncSmem<NW>;
@@ -149,10 +182,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float *lut = reinterpret_cast<float *>(smem + L::LUT);
     uint64_t *bar_a = reinterpret_cast<uint64_t *>(smem + L::BAR), *bar_mma = bar_a + 1, *bar_free = bar_a + 3;
-    uint64_t *bar_full = bar_a + 5;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 7);
-    int *sel = reinterpret_cast<int *>(bar_a + 8);   // front scratch: 4 ints
-    int *n_s = reinterpret_cast<int *>(bar_a + 10);  // [0..1] requests of the tile in buffer 0 / 1 (-1: no more tiles),
+    uint64_t *bar_full = bar_a + 5, *bar_ent = bar_a + 7;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 9);
+    int *sel = reinterpret_cast<int *>(bar_a + 10);  // front scratch: 4 ints
+    int *n_s = reinterpret_cast<int *>(bar_a + 12);  // [0..1] requests of the tile in buffer 0 / 1 (-1: no more tiles),
                                                      // [2..3] 1 if that tile waits for an operand fetch
     uint32_t *row_s = reinterpret_cast<uint32_t *>(smem + L::ROW);
     uint32_t *slot_s = reinterpret_cast<uint32_t *>(smem + L::SLOT);
@@ -168,6 +201,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         umma::mbar_init(bar_free + 1, NSVC);
         umma::mbar_init(bar_full, 1);
         umma::mbar_init(bar_full + 1, 1);
+        umma::mbar_init(bar_ent, 1);
+        umma::mbar_init(bar_ent + 1, 1);
         umma::fence_mbar_init();
     }
     umma::tc_fence_before();
@@ -277,7 +312,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             if (n < 0) {  // tell the back team to leave
                 if (tid == 0) {
                     n_s[b] = -1;
-                    mbar_arrive(bar_full + b);
+                    mbar_arrive(bar_ent + b);
                 }
                 break;
             }
@@ -306,7 +341,10 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 row_b[tid] = (uint32_t)e;
                 slot_b[tid] = (uint32_t)(e >> 32);
             }
-            if (tid == 0) n_s[b] = n;
+            if (tid == 0) {
+                n_s[b] = n;
+                n_s[2 + b] = (c != cur_c) ? 1 : 0;  // the tile switches the community: its operand images will be in flight
+            }
             // the previous tile's MMAs have read the B operand (and A) completely before either is overwritten
             if (t >= 1) umma::mbar_wait(bar_mma + ((t - 1u) & 1u), ((t - 1u) >> 1) & 1u);
             a_pending = false;
@@ -325,43 +363,14 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
             front_barrier();
             lap(1);
-            // ---- B operand: 16 rows per warp, gathers in flight GB at a time ---------------------------------------------------
-            {
-                constexpr int GB = NW * 32 > 768 ? 4 : 8;  // fewer in flight when the team runs on 48 registers
-                const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
-#pragma unroll
-                for (int half = 0; half < 16 / GB; half++) {
-                    float4 xv[GB];
-#pragma unroll
-                    for (int qq = 0; qq < GB; qq++) {
-                        const int r = warp + NSVC * (half * GB + qq);
-                        if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_b[r] * D + 4 * lane));
-                    }
-#pragma unroll
-                    for (int qq = 0; qq < GB; qq++) {
-                        const int r = warp + NSVC * (half * GB + qq);
-                        if (r < n) {
-                            const float4 x = xv[qq];
-                            const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
-                            const float4 hi = make_float4(umma::tf32_round(df.x), umma::tf32_round(df.y),
-                                                          umma::tf32_round(df.z), umma::tf32_round(df.w));
-                            const float4 lo = make_float4(umma::tf32_round(df.x - hi.x), umma::tf32_round(df.y - hi.y),
-                                                          umma::tf32_round(df.z - hi.z), umma::tf32_round(df.w - hi.w));
-                            const uint32_t off = umma::sw128_offset(TN, r, 4 * lane);
-                            *reinterpret_cast<float4 *>(smem + L::B_HI + off) = hi;
-                            *reinterpret_cast<float4 *>(smem + L::B_LO + off) = lo;
-                        }
-                    }
-                }
-            }
+            if (tid == 0) mbar_arrive(bar_ent + b);  // the back team may start on its half of the rows
+            // ---- B operand, this team's half (rows w, w+8, ...): gathers in flight 4 at a time -----------------------------
+            gather_rows<4>(P, smem + L::B_HI, smem + L::B_LO, row_b, mu_s, warp, n, lane);
             umma::fence_proxy_async_smem();
             front_barrier();
             lap(2);
-            if (tid == 0) {  // hand the tile to the back team, which issues the MMAs (their issue blocks the issuing thread
-                             // for about the MMAs' duration: off this team's critical path)
-                n_s[2 + b] = a_pending ? 1 : 0;
-                mbar_arrive(bar_full + b);
-            }
+            if (tid == 0) mbar_arrive(bar_full + b);  // this half of the B operand is in place; the back team issues the MMAs
+                                                      // (issuing blocks the thread for about their duration: off this path)
             a_pending = false;
             t++;
             tiles++;
@@ -388,11 +397,17 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         long long t_wait = 0, t_epi = 0, tq = clock64();
         for (uint32_t u = 0;; u++) {
             const uint32_t b = u & 1u;
-            umma::mbar_wait(bar_full + b, (u >> 1) & 1u);  // the front team has stored the tile's B operand and lists
+            umma::mbar_wait(bar_ent + b, (u >> 1) & 1u);  // the front team has popped the tile's entries (rows, slots, mu_c)
             const int n = n_s[b];
             if (n < 0) break;
             { const long long now = clock64(); t_wait += now - tq; tq = now; }
             const int n16 = (n + 15) & ~15;
+            // the other half of the B operand (rows 4+w, 12+w, ...); the previous tile's MMAs were waited for below
+            gather_rows<4>(P, smem + L::B_HI, smem + L::B_LO, row_s + b * TN, reinterpret_cast<const float *>(smem + L::MU), NSVC + bw,
+                           n, lane);
+            umma::fence_proxy_async_smem();
+            back_barrier();
+            umma::mbar_wait(bar_full + b, (u >> 1) & 1u);  // ... and the front team's half
             if (bw == 0) {
                 if (n_s[2 + b]) {  // this tile switched the community: its operand images are still in flight
                     umma::mbar_wait(bar_a, par_a);
