@@ -394,7 +394,13 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
         const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
         uint32_t par_a = 0;
-        long long t_wait = 0, t_epi = 0, tq = clock64();
+        long long t_wait = 0, t_epi = 0, tq = clock64(), bph[4] = {0, 0, 0, 0};
+        auto blap = [&](int k) {
+            const long long now = clock64();
+            bph[k] += now - tq;
+            t_epi += now - tq;
+            tq = now;
+        };
         for (uint32_t u = 0;; u++) {
             const uint32_t b = u & 1u;
             umma::mbar_wait(bar_ent + b, (u >> 1) & 1u);  // the front team has popped the tile's entries (rows, slots, mu_c)
@@ -407,6 +413,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                            n, lane);
             umma::fence_proxy_async_smem();
             back_barrier();
+            blap(0);
             umma::mbar_wait(bar_full + b, (u >> 1) & 1u);  // ... and the front team's half
             if (bw == 0) {
                 if (n_s[2 + b]) {  // this tile switched the community: its operand images are still in flight
@@ -422,6 +429,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
             umma::mbar_wait(bar_mma + b, (u >> 1) & 1u);
             umma::tc_fence_after();
+            blap(1);
             const uint32_t *slot_b = slot_s + b * TN;
             const int a = 32 * bw + lane;
             for (int ch = 0; ch * 16 < n16; ch++) {
@@ -435,14 +443,16 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
             umma::tc_fence_before();
             back_barrier();  // all four coordinate quarters of every result row are written ...
+            blap(2);
             if (btid < n) red_release_add_u32(P.done + slot_b[btid] / (uint32_t)P.vslots, 1u);  // ... before the counter moves
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_free + b);  // 4 arrivals: list and accumulator b are free for tile u+2
-            { const long long now = clock64(); t_epi += now - tq; tq = now; }
+            blap(3);
         }
         if (P.stats && btid == 0) {
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 14), (unsigned long long)t_wait);
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 15), (unsigned long long)t_epi);
+            for (int k = 0; k < 4; k++) atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 16 + k), (unsigned long long)bph[k]);
         }
     } else {
         // =============================== WALKER WARPS ====================================================================
@@ -727,8 +737,8 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     static const bool want_stats = getenv("COMEMB_ROUND_STATS") != nullptr;
     long long *d_stats = nullptr;
     if (want_stats) {
-        cudaMalloc(&d_stats, 16 * sizeof(long long));
-        cudaMemset(d_stats, 0, 16 * sizeof(long long));
+        cudaMalloc(&d_stats, 24 * sizeof(long long));
+        cudaMemset(d_stats, 0, 24 * sizeof(long long));
     }
     P.stats = d_stats;
     switch (negative) {
@@ -741,7 +751,7 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
         default: e = launch_async_t<7>(P, atomic, grid, st); break;
     }
     if (want_stats) {
-        long long h[16];
+        long long h[24];
         int h_err = 0;
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
@@ -756,6 +766,8 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
                 "wait %lld epilogue+signal %lld\n",
                 h[8] / (h[0] + 1), h[9] / (h[0] + 1), h[10] / (h[0] + 1), h[11] / (h[0] + 1), h[12] / (h[0] + 1),
                 h[14] / (h[0] + 1), h[15] / (h[0] + 1));
+        fprintf(stderr, "[async stats] back cycles per tile: gather-half %lld wait-front+mma %lld epilogue %lld signal %lld\n",
+                h[16] / (h[0] + 1), h[17] / (h[0] + 1), h[18] / (h[0] + 1), h[19] / (h[0] + 1));
     }
     cudaFreeAsync(scratch, st);
     return (int)e;
