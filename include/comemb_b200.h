@@ -60,6 +60,8 @@ int comemb_abi_version(void);
 #define COMEMB_VARIANT_ORDERED_PIPE 7  /* ORDERED size 128 on one software-pipelined warp */
 #define COMEMB_VARIANT_ORDERED_PLAIN 8 /* ORDERED size 128 on one plain warp */
 #define COMEMB_VARIANT_GENERIC 9       /* the any-size kernels even where a size-128 specialisation exists (tests) */
+#define COMEMB_VARIANT_ORDERED_FLOW 10 /* ORDERED o2/o1 size 128 as a dataflow graph on many warps, whatever the table size */
+#define COMEMB_VARIANT_ORDERED_TEAM 11 /* ORDERED o2 size 128 on one CTA (warp per target row), whatever the table size */
 typedef struct comemb_opts {
     int32_t centres_per_unit; /* Hogwild o2: 0 = one warp per walk (the reference's per-thread granularity); > 0 = one warp
                                  per chunk of that many centres (needs max_walk_len; the chunk starts at the right position

@@ -27,10 +27,8 @@ class Context2Vec(object):
         self.atomic = atomic
         self.use_alias = use_alias
 
-    def _mode(self):
-        if self.mode is not None:
-            return {"ordered": K.MODE_ORDERED, "hogwild": K.MODE_HOGWILD}.get(self.mode, self.mode)
-        return K.MODE_ORDERED if self.workers == 1 else K.MODE_HOGWILD
+    def _mode(self, n_tokens=0):
+        return K.select_mode(self.mode, self.workers, 2 * self.window_size * int(n_tokens))
 
     def train(self, model, paths, total_nodes, alpha=1.0, node_count=0, chunksize=150):
         import torch
@@ -46,7 +44,6 @@ class Context2Vec(object):
             raise AttributeError('need the number of node')
         start = time.time()
         dev = model.node_embedding.device
-        mode = self._mode()
         if isinstance(paths, tuple) and len(paths) in (2, 3) and hasattr(paths[0], "is_cuda"):
             walks2d, lens = paths[0], paths[1]  # device walker output: [n, L] padded with TOKEN_NONE
             if len(paths) == 3:  # CSR rows of that graph -> table rows
@@ -69,6 +66,7 @@ class Context2Vec(object):
             walks = torch.from_numpy(flat.view(np.int32)).to(dev)
             off = torch.from_numpy(off_h).to(dev)
         K.check_row_tokens(walks, model.vocab_size)
+        mode = self._mode(walks.numel())
         seeds = torch.from_numpy(K.draw_seeds(n_walks).view(np.int64)).to(dev)  # pyx:477, path order
         flags = 0
         alias = None

@@ -3,9 +3,12 @@
 Same constructor and `train(model, edges, chunksize, iter)` / `loss(model, edges)`.  The reference feeds one edge at a
 time to train_o1 from `workers` threads; here the whole (repeated) edge list is one kernel launch:
     workers == 1 -> ORDERED mode: the reference's sequential result, bit for bit (seeds drawn from np.random in edge
-                    order exactly as the single worker thread does);
+                    order exactly as the single worker thread does) -- for calls of up to
+                    K.ORDERED_AUTO_MAX_UPDATES pair updates; the sequential replay is latency-bound (~1e6 updates/s
+                    whatever the hardware), so larger calls train lock-free unless
+                    mode="ordered" is given;
     workers  > 1 -> HOGWILD mode: lock-free, one warp per edge (the reference's multi-thread semantics at GPU width).
-`mode=` overrides that choice.
+`mode=` ("ordered" | "hogwild") overrides that choice (K.select_mode).
 """
 import logging as log
 import time
@@ -25,10 +28,8 @@ class Node2Vec(object):
         self.mode = mode
         self.atomic = atomic
 
-    def _mode(self):
-        if self.mode is not None:
-            return {"ordered": K.MODE_ORDERED, "hogwild": K.MODE_HOGWILD}.get(self.mode, self.mode)
-        return K.MODE_ORDERED if self.workers == 1 else K.MODE_HOGWILD
+    def _mode(self, n_edges=0):
+        return K.select_mode(self.mode, self.workers, 2 * int(n_edges))
 
     def loss(self, model, edges):
         """-sum log sigmoid(x_u . x_v) over in-vocabulary edges (node_embeddings.py:26-31), on the device."""
@@ -55,7 +56,7 @@ class Node2Vec(object):
             keep = np.repeat(lens == 2, lens)
             flat = flat[keep]
         n_edges = flat.size // 2
-        mode = self._mode()
+        mode = self._mode(n_edges)
         dev = model.node_embedding.device
         e = torch.from_numpy(flat.view(np.int32)).to(dev)
         K.check_row_tokens(e, model.vocab_size, "edge endpoints")

@@ -61,7 +61,7 @@ class ComembOpts(ctypes.Structure):
 
 
 (VARIANT_DEFAULT, VARIANT_ROUNDSYNC, VARIANT_TENSOR, VARIANT_L2_HINTS, VARIANT_ROUND1, VARIANT_ORDERED_PIPE,
- VARIANT_ORDERED_PLAIN, VARIANT_GENERIC) = (0, 3, 4, 5, 6, 7, 8, 9)
+ VARIANT_ORDERED_PLAIN, VARIANT_GENERIC, VARIANT_ORDERED_FLOW, VARIANT_ORDERED_TEAM) = (0, 3, 4, 5, 6, 7, 8, 9, 10, 11)
 
 
 class ComembError(RuntimeError):

@@ -16,11 +16,13 @@
 //   o2_ordered_d128_team_kernel (default for o2, window <= 15)      scheduling warp + one worker warp per target row
 // They all produce the same bits (tests/test_gpu_parity.py::test_o2_ordered_d128_kernel_variants_hazards).
 #include "comemb_common.cuh"
+#include "ordered_d128.cuh"
 // comemb_opts().variant selects among the size-128 ORDERED kernels: default = one worker warp per target row (o2) /
 // pipelined single warp (o1); ORDERED_PIPE = single warp, software-pipelined; ORDERED_PLAIN = single warp, plain;
 // GENERIC = the any-size kernels.
 
 namespace {
+using namespace ordered;
 
 // ---- dot product in the reference's summation order ---------------------------------------------------------------------
 // x, y: rows in global memory, previously written (possibly by other lanes of this warp) and made visible by
@@ -75,11 +77,6 @@ __device__ float dot_refblas(const float *x, const float *y, int n, bool quirk) 
 __device__ __forceinline__ void axpy_rows(int n, float a, const float *x, float *y) {
     for (int e = threadIdx.x & 31; e < n; e += 32) y[e] = fmaf(a, x[e], y[e]);
 }
-
-struct Sampler {
-    const uint32_t *table;
-    TableMod mod;
-};
 
 // fast_o2 (pyx:105-151).  work: shared memory [size].
 __device__ uint64_t pair_o2(const Sampler &S, float *node, float *ctx, int size, uint32_t word_index,
@@ -188,38 +185,6 @@ __global__ void __launch_bounds__(32) o2_ordered_kernel(float *node, float *ctx,
 // q mod 32), the NEG+1 rows of a pair are gathered together, the positive context row stays in registers across the
 // centre's window, samples are fetched one pair ahead.  Every floating-point operation and its association order is
 // the one of dot_refblas()/axpy_rows() above, so the tables stay bit-identical to the reference.
-struct Row4 {
-    float v0, v1, v2, v3;  // elements t, t+32, t+64, t+96
-};
-__device__ __forceinline__ Row4 ld_row4(const float *row, int lane) {
-    Row4 r;
-    r.v0 = row[lane]; r.v1 = row[lane + 32]; r.v2 = row[lane + 64]; r.v3 = row[lane + 96];
-    return r;
-}
-__device__ __forceinline__ void st_row4(float *row, int lane, const Row4 &r) {
-    row[lane] = r.v0; row[lane + 32] = r.v1; row[lane + 64] = r.v2; row[lane + 96] = r.v3;
-}
-// dot of two 128-element rows in the reference's order (see dot_refblas): value on every lane
-__device__ __forceinline__ float dot128_refblas(const Row4 &x, const Row4 &y, bool quirk) {
-    float a0 = fmaf(x.v2, y.v2, fmaf(x.v0, y.v0, 0.f));  // accumulator q = t      : elements t, t+64
-    float a1 = fmaf(x.v3, y.v3, fmaf(x.v1, y.v1, 0.f));  // accumulator q = t + 32 : elements t+32, t+96
-    a0 = a0 + __shfl_down_sync(FULL, a0, 8);
-    a1 = a1 + __shfl_down_sync(FULL, a1, 8);
-    float v = a0 + __shfl_down_sync(FULL, a0, 16);
-    v = v + a1;
-    v = v + __shfl_down_sync(FULL, a1, 16);
-    const float h = v + __shfl_down_sync(FULL, v, 4);
-    const float p = h + __shfl_down_sync(FULL, h, 1);
-    float my = p + __shfl_down_sync(FULL, p, 2);
-    my = __shfl_sync(FULL, my, 0);
-    if (!quirk) return my;  // (float)(0.0 + (double)my) == my
-    const double dot = (double)my;
-    return __double2float_rn(__hiloint2double(__double2hiint(dot), __float_as_int(my)));
-}
-__device__ __forceinline__ void fma_row4(Row4 &y, float a, const Row4 &x) {
-    y.v0 = fmaf(a, x.v0, y.v0); y.v1 = fmaf(a, x.v1, y.v1); y.v2 = fmaf(a, x.v2, y.v2); y.v3 = fmaf(a, x.v3, y.v3);
-}
-
 template <int NEG>
 __global__ void __launch_bounds__(32)
     o2_ordered_d128_kernel(float *node, float *ctx, const uint32_t *walks, const int64_t *walk_off, int64_t n_walks,
@@ -1153,12 +1118,23 @@ __global__ void __launch_bounds__(32)
 }  // namespace
 
 // ---- launchers (called from capi.cu) -------------------------------------------------------------------------------------
+int launch_o2_flow(float *, float *, int64_t, const uint32_t *, const int64_t *, int64_t, const uint64_t *, uint64_t,
+                   const uint32_t *, uint64_t, int, int, float, float, bool, int64_t *, int, cudaStream_t);  // sgns_flow.cu
 int launch_o2_ordered(float *node, float *ctx, int64_t n_rows, int size, const uint32_t *walks, const int64_t *walk_off,
                       int64_t n_walks, const uint64_t *seeds, uint64_t base_seed, const uint32_t *table,
                       uint64_t table_len, int window, int negative, float lr, float lambda, bool quirk, int64_t *n_tokens,
                       cudaStream_t st) {
     Sampler S{table, make_table_mod(table_len)};
     const bool disjoint = node + n_rows * size <= ctx || ctx + n_rows * size <= node;
+    const int variant = comemb_opts().variant;
+    if (size == 128 && disjoint && variant == COMEMB_VARIANT_ORDERED_FLOW) {
+        // the same stream as a dataflow graph over many warps (sgns_flow.cu), same bits.  Opt-in: on the walk corpora
+        // of BASELINE.json the stream's dependency chain leaves 1.1-1.5x of parallelism and a
+        // pair costs one warp 2.9 us against 0.72 us on the one-CTA team below.
+        const int rc = launch_o2_flow(node, ctx, n_rows, walks, walk_off, n_walks, seeds, base_seed, table, table_len, window,
+                                      negative, lr, lambda, quirk, n_tokens, comemb_opts().max_warps, st);
+        if (rc != COMEMB_E_UNSUPPORTED) return rc;
+    }
     if (size == 128 && comemb_opts().variant != COMEMB_VARIANT_GENERIC && disjoint && !(comemb_opts().variant == COMEMB_VARIANT_ORDERED_PIPE || comemb_opts().variant == COMEMB_VARIANT_ORDERED_PLAIN) &&
         window <= TEAM_MAX_WINDOW) {  // warp per target row + scheduling warp, same bits
         switch (negative) {

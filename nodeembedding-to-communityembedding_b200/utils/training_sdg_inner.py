@@ -151,6 +151,29 @@ def hogwild_concurrency(n_rows, workers=1):
     return int(max(int(workers), int(n_rows) // 28, 1))
 
 
+# The ORDERED replay is bound by the dependency chain of the update stream, not by the GPU: on the walk corpora of
+# BASELINE.json consecutive walks share ~15 rows, the longest dependency path covers 68-91 % of all pairs (DESIGN.md
+# section 6, scripts/ordered_critical_path.py), and the replay runs at ~1.4e6 pair updates/s.  A learner built with
+# workers=1 and no explicit mode therefore replays the reference's order only up to this many updates (about a second
+# and a half) and trains larger corpora lock-free like the reference's workers>1; mode="ordered" always replays.
+ORDERED_AUTO_MAX_UPDATES = 2000000
+
+
+def select_mode(mode, workers, n_updates):
+    """The learners' mode rule.  mode: None | "ordered" | "hogwild" | MODE_*; n_updates: upper bound of the pair
+    updates of the call (o2: tokens * 2 * window; o1: 2 * edges)."""
+    if mode is not None:
+        return {"ordered": MODE_ORDERED, "hogwild": MODE_HOGWILD}.get(mode, mode)
+    if workers == 1 and n_updates <= ORDERED_AUTO_MAX_UPDATES:
+        return MODE_ORDERED
+    if workers == 1:
+        import logging
+        logging.getLogger(__name__).info(
+            "workers=1 with %d pair updates (> %d): training lock-free; pass mode=\"ordered\" for the reference's "
+            "sequential order bit for bit (~1.4e6 updates/s)", n_updates, ORDERED_AUTO_MAX_UPDATES)
+    return MODE_HOGWILD
+
+
 class _max_warps(object):
     """Concurrency cap for the launches inside the block; the caller's previous cap is restored afterwards."""
 

@@ -76,13 +76,14 @@ def test_o2_ordered_generic_kernel_at_d128(K, golden, name):
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
 
 
-@pytest.mark.parametrize("variant", [0, 700, 800])
+@pytest.mark.parametrize("variant", [0, 700, 800, 1000, 1100])
 @pytest.mark.parametrize("N,neg,none_every,W", [(6, 5, 0, 4), (12, 7, 5, 4), (40, 3, 0, 4), (40, 1, 3, 2), (3000, 5, 0, 10),
                                                 (3000, 2, 7, 15), (3000, 6, 0, 1), (40, 5, 0, 16), (3000, 5, 4, 20)])
 def test_o2_ordered_d128_kernel_variants_hazards(K, variant, N, neg, none_every, W):
-    """The three size-128 ORDERED kernels (0: scheduling warp + one worker warp per target row with two-pair look-ahead
-    -- window <= 15, wider windows take the pipelined kernel --, 7: single warp software pipelined, 8: single warp plain)
-    against the oracle, bit for bit, on inputs that hit every hazard path: tiny tables (equal samples inside a pair ->
+    """The size-128 ORDERED kernels (0: default for the shape; 11: scheduling warp + one worker warp per target row with
+    two-pair look-ahead -- window <= 15, wider windows take the pipelined kernel --, 7: single warp software pipelined,
+    8: single warp plain, 10: the dataflow replay on one warp per walk, csrc/sgns_flow.cu, where tiny tables make
+    nearly every touch wait for another walk) against the oracle, bit for bit, on inputs that hit every hazard path: tiny tables (equal samples inside a pair ->
     serial path; samples equal to rows of the pairs in flight -> re-read; repeated walk tokens -> register forwarding),
     None tokens, ragged and empty walks, pair streams that end exactly on / around a 32-pair chunk boundary, and a table
     large enough for the clean path."""
@@ -104,6 +105,53 @@ def test_o2_ordered_d128_kernel_variants_hazards(K, variant, N, neg, none_every,
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
     O.o2_walks(node, ctx, flat, off, seeds, c["lr"], neg, c["W"], table, lam, O.DOT_REFBLAS_QUIRK)
     assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+
+
+@pytest.mark.parametrize("max_warps", [0, 1, 3, 64])
+@pytest.mark.parametrize("N,nw,L,neg,W,none_every", [(64, 300, 20, 5, 5, 0), (2000, 400, 40, 5, 5, 9), (2000, 300, 30, 7, 12, 0),
+                                                     (20000, 600, 40, 3, 4, 0), (300, 200, 25, 1, 2, 4)])
+def test_o2_flow_kernel_vs_oracle(K, N, nw, L, neg, W, none_every, max_warps):
+    """ORDERED o2 as a dataflow graph (csrc/sgns_flow.cu: per-row tickets from a stable sort of every touch, one warp per
+    walk) against the sequential oracle, bit for bit, with hundreds of walks in flight: tables from 64 rows (every
+    row contended by many walks, equal samples inside a pair) to 20 000 rows (mostly independent walks), None tokens,
+    ragged and empty walks, any number of resident warps (1 = the plain sequential order; 3; all)."""
+    from comemb_b200 import _lib
+    c = dict(cases.O2_CASES["o2_d128_small"], N=N, neg=neg, nw=nw, L=L, W=W, seed=9100 + N + neg, ragged=True)
+    if none_every:
+        c["none_every"] = none_every
+    lam = 0.7 if neg == 3 else 1.0
+    node, ctx, table, walks = cases.o2_inputs(c)
+    walks = list(walks) + [np.zeros(0, np.uint32), walks[0][:1], walks[1][:2]]
+    flat, off = cases.flatten_walks(walks)
+    seeds = O.seeds_from_numpy(np.random.RandomState(15), len(walks))
+    dn, dc = dev(node), dev(ctx)
+    with _lib.opts(variant=_lib.VARIANT_ORDERED_FLOW, max_warps=max_warps):
+        n = K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), c["lr"], neg, W, dev(table), alpha=lam, mode=K.MODE_ORDERED,
+                       count_tokens=True)
+    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], neg, W, table, lam, O.DOT_REFBLAS_QUIRK)
+    assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+    assert n == int((flat != 0xFFFFFFFF).sum())
+
+
+def test_o2_flow_kernel_equals_one_cta_replay_at_scale(K):
+    """50 000 rows, 3 000 walks of 40 (1 M pair updates): the dataflow replay and the one-CTA kernel produce the same
+    bits; hashed per-walk seeds (no seed array)."""
+    from comemb_b200 import _lib
+    rng = np.random.RandomState(77)
+    N, nw, L = 50000, 3000, 40
+    node = ((rng.rand(N, 128) - 0.5) / 128).astype(np.float32)
+    ctx = ((rng.rand(N, 128) - 0.5) / 128).astype(np.float32)
+    table = rng.randint(0, N, size=1 << 20).astype(np.uint32)
+    flat = rng.randint(0, N, size=nw * L).astype(np.uint32)
+    off = (np.arange(nw + 1) * L).astype(np.int64)
+    out = {}
+    for name, variant in (("flow", _lib.VARIANT_ORDERED_FLOW), ("team", _lib.VARIANT_DEFAULT)):
+        dn, dc = dev(node), dev(ctx)
+        with _lib.opts(variant=variant):
+            K.o2_batch(dn, dc, dev(flat), dev(off), None, 0.025, 5, 5, dev(table), mode=K.MODE_ORDERED, base_seed=123)
+        out[name] = (host(dn), host(dc))
+    assert np.array_equal(out["flow"][0], out["team"][0]) and np.array_equal(out["flow"][1], out["team"][1])
+    assert not np.array_equal(out["flow"][0], node)
 
 
 @pytest.mark.parametrize("lens", [[0, 0], [1], [1, 0, 1], [2], [16], [17], [18], [32], [33], [34], [49], [17, 0, 17],

@@ -338,3 +338,25 @@ def test_nmi_on_tensors_matches_sklearn():
     x = np.concatenate([rs.normal(size=(200, 8)) + 6 * rs.normal(size=(1, 8)) for _ in range(4)])
     lab = np.repeat(np.arange(4), 200)
     assert evaluation.community_nmi(torch.as_tensor(x, dtype=torch.float32), lab, method="device") > 0.9
+
+
+def test_learner_mode_rule():
+    """workers=1 replays the reference's order up to ORDERED_AUTO_MAX_UPDATES pair updates and trains lock-free above;
+    an explicit mode always wins; workers>1 is lock-free (utils/training_sdg_inner.select_mode)."""
+    from comemb_b200.utils import training_sdg_inner as K
+    from comemb_b200.ADSCModel.context_embeddings import Context2Vec
+    from comemb_b200.ADSCModel.node_embeddings import Node2Vec
+    big = K.ORDERED_AUTO_MAX_UPDATES
+    assert K.select_mode(None, 1, 10) == K.MODE_ORDERED
+    assert K.select_mode(None, 1, big) == K.MODE_ORDERED
+    assert K.select_mode(None, 1, big + 1) == K.MODE_HOGWILD
+    assert K.select_mode("ordered", 1, 100 * big) == K.MODE_ORDERED
+    assert K.select_mode("ordered", 8, 100 * big) == K.MODE_ORDERED
+    assert K.select_mode("hogwild", 1, 1) == K.MODE_HOGWILD
+    assert K.select_mode(None, 4, 10) == K.MODE_HOGWILD
+    assert K.select_mode(K.MODE_ORDERED, 4, 10) == K.MODE_ORDERED
+    c = Context2Vec(window_size=5, workers=1)
+    assert c._mode(1000) == K.MODE_ORDERED and c._mode(big) == K.MODE_HOGWILD
+    assert Context2Vec(workers=1, mode="ordered")._mode(big) == K.MODE_ORDERED
+    n = Node2Vec(workers=1)
+    assert n._mode(1000) == K.MODE_ORDERED and n._mode(big) == K.MODE_HOGWILD
