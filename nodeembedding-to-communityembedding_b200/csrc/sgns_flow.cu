@@ -289,12 +289,17 @@ int launch_o2_flow(float *node, float *ctx, int64_t n_rows, const uint32_t *walk
     flow_count_kernel<<<(unsigned)((n_walks + 1 + 255) / 256), 256, 0, st>>>(walks, walk_off, n_walks, window, pair_off,
                                                                               n_tokens);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, pair_off, pair_off, n_walks + 1, st);
-    CUDA_TRY(cudaMallocAsync(&scan_tmp, scan_bytes ? scan_bytes : 1, st));
-    cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, pair_off, pair_off, n_walks + 1, st);
     std::vector<int64_t> off_h((size_t)n_walks + 1);
-    CUDA_TRY(cudaMemcpyAsync(off_h.data(), pair_off, off_h.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaFreeAsync(scan_tmp, st));
+    cudaError_t e = cudaMallocAsync(&scan_tmp, scan_bytes ? scan_bytes : 1, st);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, pair_off, pair_off, n_walks + 1, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(off_h.data(), pair_off, off_h.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (scan_tmp) cudaFreeAsync(scan_tmp, st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(pair_off, st);
+        return (int)e;
+    }
 
     // chunks of whole walks with at most `cap` touches (a single longer walk forms its own chunk)
     const int64_t cap = 1LL << 27;

@@ -2,7 +2,8 @@
 micro-F1 on the learned node table, and the o1 / o2 objectives.  The objectives run on the device (Node2Vec.loss,
 comemb_o2_pos_loss; pinned against reference-generated values in tests/golden/golden_losses.json); `nmi` and
 `community_nmi(method="device")` keep the node table on the device as well (k-means assignment + contingency table in
-torch); the micro-F1 protocol (one-vs-rest logistic regression) is host-side sklearn.  Not part of the SGD path."""
+torch); the micro-F1 protocol (logistic regression on a train split) runs through sklearn on the host or, with
+method="device", as an L-BFGS fit in torch on the table's device.  Not part of the SGD path."""
 import numpy as np
 
 
@@ -58,16 +59,43 @@ def community_nmi(embedding, labels, k=None, method="gmm", seed=0):
     return float(normalized_mutual_info_score(labels, pred))
 
 
-def node_classification_micro_f1(embedding, labels, train_fraction=0.5, seed=0):
-    """One-vs-rest logistic regression on a random train split, micro-F1 on the rest (the DeepWalk protocol)."""
-    from sklearn.linear_model import LogisticRegression
-    from sklearn.metrics import f1_score
-    x = _np(embedding).astype(np.float64)
-    y = np.asarray(labels)
+def node_classification_micro_f1(embedding, labels, train_fraction=0.5, seed=0, method="sklearn", l2=1.0, max_iter=100):
+    """Logistic regression on a random train split, micro-F1 on the rest (the DeepWalk protocol).  method="sklearn":
+    host LogisticRegression; method="device": the same L2-regularised multinomial model (C = 1/l2, intercept not
+    penalised) fitted by L-BFGS in torch on the device the table lives on -- the table is never copied to the host.
+    With one label per node micro-F1 is the accuracy on the test split; both methods use the same split."""
+    y = np.asarray(_np(labels))
     rs = np.random.RandomState(seed)
     perm = rs.permutation(len(y))
     cut = int(train_fraction * len(y))
     tr, te = perm[:cut], perm[cut:]
+    if method == "device":
+        import torch
+        x = embedding if isinstance(embedding, torch.Tensor) else torch.as_tensor(np.asarray(embedding))
+        x = x.detach().double()
+        dev = x.device
+        classes, yi = np.unique(y, return_inverse=True)
+        yt = torch.from_numpy(yi).to(dev)
+        tr_t, te_t = torch.from_numpy(tr).to(dev), torch.from_numpy(te).to(dev)
+        xtr, ytr = x[tr_t], yt[tr_t]
+        w = torch.zeros((x.shape[1], len(classes)), dtype=torch.float64, device=dev, requires_grad=True)
+        b = torch.zeros(len(classes), dtype=torch.float64, device=dev, requires_grad=True)
+        opt = torch.optim.LBFGS([w, b], lr=1.0, max_iter=max_iter, tolerance_grad=1e-6, tolerance_change=1e-10,
+                                history_size=10, line_search_fn="strong_wolfe")
+
+        def closure():  # sklearn's objective: C * sum_i loss_i + 0.5 ||w||^2 with C = 1 / l2
+            opt.zero_grad()
+            loss = torch.nn.functional.cross_entropy(xtr @ w + b, ytr, reduction="sum") / l2 + 0.5 * (w * w).sum()
+            loss.backward()
+            return loss
+
+        opt.step(closure)
+        with torch.no_grad():
+            pred = (x[te_t] @ w + b).argmax(1)
+            return float((pred == yt[te_t]).double().mean())
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.metrics import f1_score
+    x = _np(embedding).astype(np.float64)
     clf = LogisticRegression(max_iter=500).fit(x[tr], y[tr])
     return float(f1_score(y[te], clf.predict(x[te]), average="micro"))
 

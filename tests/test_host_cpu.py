@@ -360,3 +360,19 @@ def test_learner_mode_rule():
     assert Context2Vec(workers=1, mode="ordered")._mode(big) == K.MODE_ORDERED
     n = Node2Vec(workers=1)
     assert n._mode(1000) == K.MODE_ORDERED and n._mode(big) == K.MODE_HOGWILD
+
+
+def test_micro_f1_device_method_matches_sklearn():
+    """evaluation.node_classification_micro_f1(method="device") -- multinomial logistic regression by L-BFGS in torch --
+    against the sklearn path on the same split: overlapping Gaussian blobs (so that the score is not trivially 1)."""
+    import torch
+    from comemb_b200.evaluation import node_classification_micro_f1
+    rs = np.random.RandomState(3)
+    k, n, d = 5, 1500, 16
+    centres = rs.randn(k, d) * 0.9
+    y = rs.randint(0, k, size=n)
+    x = (centres[y] + rs.randn(n, d)).astype(np.float32)
+    a = node_classification_micro_f1(x, y, seed=1)
+    b = node_classification_micro_f1(torch.from_numpy(x), y, seed=1, method="device")
+    assert 0.5 < a < 0.999
+    assert abs(a - b) <= 0.01, (a, b)
