@@ -151,6 +151,13 @@ int comemb_o3_batch_top1(float *d_node, int64_t n_rows, int size, const uint32_t
  * [n, K] result reaches memory.  Other sizes: COMEMB_E_UNSUPPORTED (the caller uses a library GEMM). */
 int comemb_gmm_estep(const float *d_x, int64_t n, int size, const float *d_prec_chol, const float *d_bias, int K,
                      float *d_sq, void *stream);
+/* ---- GMM M-step, covariance part (sklearn _estimate_gaussian_covariances_full before the division by n_k) ------------------
+ *    d_scatter[k][a][b] = sum_n d_resp[n][k] (x_n[a] - mu_k[a]) (x_n[b] - mu_k[b])        d_means = mu, [K][size]
+ * size 128: tcgen05 3xTF32, four components per CTA accumulate in TMEM, the centred / weighted tiles are built in shared
+ * memory -- no [K, n, size] temporary.  Tiles whose 32 responsibilities for a component are all exactly 0 are skipped.
+ * Other sizes: COMEMB_E_UNSUPPORTED (the caller uses library GEMMs). */
+int comemb_gmm_mstep(const float *d_x, int64_t n, int size, const float *d_resp, const float *d_means, int K,
+                     float *d_scatter, void *stream);
 /* out[k][b][a] = in[k][a][b] for K blocks of size x size */
 int comemb_transpose_blocks(const float *d_in, float *d_out, int K, int size, void *stream);
 

@@ -8,8 +8,10 @@ outer iteration once o1/o2/o3 run at GPU speed.  This class restates sklearn's E
 E-step -- the dominant 2*N*K*d^2 contraction -- is the hand-written tcgen05 kernel comemb_gmm_estep at d == 128 in fp32
 (csrc/o3_gemm.cu: P_k resident in shared memory as the 3xTF32 A operand, points streamed as 64-row tiles, squared norm
 reduced in the epilogue, only [N, K] written); the fallback (other sizes, float64, CPU) is one library GEMM [N,d] x [d,K*d]
-per row block.  The M-step's covariances are batched library GEMMs ([kc,d,N] x [kc,N,d]; cuBLAS) and the precision factors
-batched Cholesky / triangular solves (cuSOLVER / cuBLAS).
+per row block.  The M-step's covariances are the hand-written tcgen05 kernel comemb_gmm_mstep
+under the same condition (csrc/gmm_mstep.cu: four components per CTA accumulate in TMEM, centred / weighted point tiles built
+in shared memory, no [K, N, d] temporary), otherwise batched library GEMMs ([kc,d,N] x [kc,N,d]; cuBLAS); the precision
+factors are batched Cholesky / triangular solves (cuSOLVER / cuBLAS).
 
 Parity: given the same initial responsibilities the iterations follow sklearn's to fp32 round-off
 (tests/test_gmm_device.py, CPU and GPU).  The initialisation differs (own k-means++ / Lloyd instead of sklearn's KMeans
@@ -22,7 +24,8 @@ import numpy as np
 
 class DeviceGaussianMixture(object):
     def __init__(self, n_components=1, reg_covar=1e-6, tol=1e-3, max_iter=100, n_init=1, random_state=None,
-                 dtype=None, kmeans_iter=20, workspace_bytes=6 << 30, tf32=False, sparse_m_step=True, estep_kernel=True):
+                 dtype=None, kmeans_iter=20, workspace_bytes=6 << 30, tf32=False, sparse_m_step=True, estep_kernel=True,
+                 mstep_kernel=True):
         self.n_components = int(n_components)
         self.reg_covar = float(reg_covar)
         self.tol = float(tol)
@@ -34,6 +37,7 @@ class DeviceGaussianMixture(object):
         self.workspace_bytes = int(workspace_bytes)  # bound on the temporaries of the batched E / M steps
         self.sparse_m_step = bool(sparse_m_step)
         self.estep_kernel = bool(estep_kernel)  # fp32, d == 128 on CUDA: the tcgen05 E-step kernel instead of the library GEMM
+        self.mstep_kernel = bool(mstep_kernel)  # same condition: the tcgen05 covariance kernel instead of the batched GEMMs
         self.tf32 = bool(tf32)  # let cuBLAS use TF32 tensor cores for the fp32 GEMMs (about 1.7x per EM iteration;
         #                         the sklearn comparison of tests/test_gmm_device.py holds for tf32=False)
         self.converged_ = False
@@ -51,7 +55,17 @@ class DeviceGaussianMixture(object):
         K, d = means.shape
         n = X.shape[0]
         covs = None
-        if self.sparse_m_step and n * K >= (1 << 16):
+        if self.mstep_kernel and X.is_cuda and X.dtype == torch.float32 and d == 128 and n > 0:
+            # hand-written covariance kernel (csrc/gmm_mstep.cu, comemb_gmm_mstep): the centred / weighted tiles are
+            # built in shared memory, four components per CTA accumulate in TMEM -- no [K, n, d] temporary, no host sync
+            from .. import _lib
+            covs = torch.empty((K, d, d), dtype=X.dtype, device=X.device)
+            xc, rc, mc = X.contiguous(), resp.contiguous(), means.contiguous()
+            with torch.cuda.device(X.device):
+                _lib.check(_lib.load().comemb_gmm_mstep(_lib.ptr(xc), n, d, _lib.ptr(rc), _lib.ptr(mc), K, _lib.ptr(covs),
+                                                        _lib.stream_ptr()))
+            covs /= nk[:, None, None]
+        if covs is None and self.sparse_m_step and n * K >= (1 << 16):
             covs = self._covariances_sparse(X, resp, nk, means)
         if covs is None:
             covs = torch.empty((K, d, d), dtype=X.dtype, device=X.device)

@@ -40,6 +40,7 @@ SIGNATURES = {
                                     _i32, _i32, _i32, _f32, _f32, _f32, _u32, _vp]),
     "comemb_transpose_blocks": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "comemb_gmm_estep": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "comemb_gmm_mstep": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
     "comemb_sg_fused": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _i32,
                                _i32, _i32, _f32, _f32, _f32, _i32, _i32, _u32, _vp]),
     "comemb_sg_twin": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _f64, _f64, _f64, _vp, _vp, _vp, _i32, _i32,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libcomemb_b200.so")
-SOURCES = ["capi.cu", "sgns_ordered.cu", "sgns_flow.cu", "sgns_hogwild.cu", "fused_sg.cu", "fused_round.cu", "fused_async.cu", "o3_community.cu", "o3_gemm.cu", "walker.cu",
+SOURCES = ["capi.cu", "sgns_ordered.cu", "sgns_flow.cu", "sgns_hogwild.cu", "fused_sg.cu", "fused_round.cu", "fused_async.cu", "o3_community.cu", "o3_gemm.cu", "gmm_mstep.cu", "walker.cu",
            "sampler.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]

@@ -31,6 +31,7 @@ int launch_o3_batch(float *, int64_t, int, const uint32_t *, int64_t, const floa
                     const int32_t *, const float *, int, double, float, int, cudaStream_t);
 int launch_transpose_blocks(const float *, float *, int, int, cudaStream_t);
 int launch_gmm_estep(const float *, int64_t, const float *, const float *, int, float *, cudaStream_t);
+int launch_gmm_mstep(const float *, int64_t, const float *, const float *, int, float *, cudaStream_t);  // gmm_mstep.cu
 int launch_scale(float *, int64_t, float, cudaStream_t);
 int launch_row_probe(float *, int64_t, int, float *, cudaStream_t);
 int launch_o2_pos_loss(const float *, const float *, int, const uint32_t *, const int64_t *, int64_t, int, double *,
@@ -260,6 +261,13 @@ int comemb_gmm_estep(const float *d_x, int64_t n, int size, const float *d_prec_
     if (!d_x || !d_prec_chol || !d_bias || !d_sq || n < 0 || K <= 0) return COMEMB_E_ARG;
     if (size != 128) return COMEMB_E_UNSUPPORTED;
     return launch_gmm_estep(d_x, n, d_prec_chol, d_bias, K, d_sq, (cudaStream_t)stream);
+}
+
+int comemb_gmm_mstep(const float *d_x, int64_t n, int size, const float *d_resp, const float *d_means, int K,
+                     float *d_scatter, void *stream) {
+    if (!d_x || !d_resp || !d_means || !d_scatter || n < 0 || K <= 0) return COMEMB_E_ARG;
+    if (size != 128) return COMEMB_E_UNSUPPORTED;
+    return launch_gmm_mstep(d_x, n, d_resp, d_means, K, d_scatter, (cudaStream_t)stream);
 }
 
 int comemb_transpose_blocks(const float *d_in, float *d_out, int K, int size, void *stream) {
