@@ -5,7 +5,7 @@
 // runs as [kc, d, N] x [kc, N, d] batched GEMMs over two materialised [K, N, d] temporaries (5 GB at N=1e5, K=50).
 //
 // Here one CTA owns 4 components (their four 128 x 128 fp32 accumulators fill the SM's 512 TMEM columns) and a strided
-// share of the 32-point tiles.  A tile's points are read once into registers (thread = one point x 16 features); for each
+// share of the 32-point tiles.  A tile's points are read once into registers (thread = one point x 8 features); for each
 // of the 4 components the CTA writes the transposed, centred tile  B[b][i] = x_i[b] - mu_k[b]  and its weighted copy
 // A[a][i] = r_ik B[a][i]  as 3xTF32 hi/lo images in the K-major SWIZZLE_128B layout (K = the point index: 32 points =
 // one 128-byte swizzle row, lanes = points -> conflict-free stores) and one thread issues
@@ -22,7 +22,9 @@ namespace {
 constexpr int D = 128;
 constexpr int TP = 32;  // points per tile = one K-atom
 constexpr int CG = 4;   // components per CTA: 4 x 128 TMEM columns
-constexpr int WARPS = 8;
+constexpr int WARPS = 16;
+constexpr int FPT = D / WARPS;  // features per thread
+constexpr int NV = FPT / 4;     // float4 loads per thread and tile
 constexpr int IMG = D * TP * 4;  // one [128 features x 32 points] image: 16 KB
 constexpr int STAGE = 4 * IMG;   // A_hi, A_lo, B_hi, B_lo
 constexpr int SMEM_MU = 2 * STAGE;
@@ -63,18 +65,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gmm_mstep_kernel(const MstepPar
     const int64_t tiles = (P.n + TP - 1) / TP;
     const uint32_t idesc = umma::idesc_tf32_m128(D);
 
-    float4 xv[4], xn[4];
+    float4 xv[NV], xn[NV];
     float wv[CG], wn[CG];
-    auto load = [&](int64_t t, float4(&xx)[4], float(&ww)[CG]) {  // thread = point `lane` of the tile, features 16*warp..+15
+    auto load = [&](int64_t t, float4(&xx)[NV], float(&ww)[CG]) {  // thread = point `lane` of the tile, features FPT*warp..
         const int64_t i = t * TP + lane;
         if (i < P.n) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) xx[q] = __ldg(reinterpret_cast<const float4 *>(P.x + i * D + 16 * warp + 4 * q));
+            for (int q = 0; q < NV; q++) xx[q] = __ldg(reinterpret_cast<const float4 *>(P.x + i * D + FPT * warp + 4 * q));
 #pragma unroll
             for (int c = 0; c < CG; c++) ww[c] = c < nc ? __ldg(P.resp + i * P.K + k0 + c) : 0.f;
         } else {
 #pragma unroll
-            for (int q = 0; q < 4; q++) xx[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < NV; q++) xx[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < CG; c++) ww[c] = 0.f;
         }
@@ -95,13 +97,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gmm_mstep_kernel(const MstepPar
             if (batch >= 2) umma::mbar_wait(&bar_mma[s], ((batch >> 1) - 1u) & 1u);  // the previous use of this stage
             char *stg = smem + s * STAGE;
             const float w = wv[c];
-            const float *mu = mu_s + c * D + 16 * warp;
+            const float *mu = mu_s + c * D + FPT * warp;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < NV; q++) {
                 const float xs[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const int a = 16 * warp + 4 * q + e;
+                    const int a = FPT * warp + 4 * q + e;
                     const float dv = xs[e] - mu[4 * q + e];
                     const float av = w * dv;  // a tail point (beyond n) has w = 0: its A column is 0, B's does not matter
                     const float dh = umma::tf32_round(dv), ah = umma::tf32_round(av);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gmm_mstep_kernel(const MstepPar
             batch++;
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) xv[q] = xn[q];
+        for (int q = 0; q < NV; q++) xv[q] = xn[q];
 #pragma unroll
         for (int c = 0; c < CG; c++) wv[c] = wn[c];
     }
@@ -144,15 +146,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gmm_mstep_kernel(const MstepPar
     if (batch >= 1) umma::mbar_wait(&bar_mma[(batch - 1) & 1u], ((batch - 1) >> 1) & 1u);
     umma::tc_fence_after();
     {
-        // accumulator row a = TMEM lane; warps w and w+4 share a lane quarter and split the 128 columns
+        // accumulator row a = TMEM lane; the WARPS/4 warps of a lane quarter split the 128 columns
+        constexpr int COLS = D / (WARPS / 4);
         const int a = 32 * (warp & 3) + lane;
         for (int c = 0; c < nc; c++) {
             if (!((started >> c) & 1u)) continue;
-            float *dst = P.scatter + ((int64_t)(k0 + c) * D + a) * D + 64 * (warp >> 2);
+            float *dst = P.scatter + ((int64_t)(k0 + c) * D + a) * D + COLS * (warp >> 2);
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ch++) {
+            for (int ch = 0; ch < COLS / 16; ch++) {
                 float v[16];
-                umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(c * D + 64 * (warp >> 2) + 16 * ch), v);
+                umma::tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(c * D + COLS * (warp >> 2) + 16 * ch), v);
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     red_add4(dst + 16 * ch + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
