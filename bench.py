@@ -627,7 +627,7 @@ def secondary_sg(wl, Kc, n_walks, flush, lam2=0.1):
     peak, _ = measured_peak()
     return {"metric": "fused_sg_pair_updates_per_sec", "value": v, "unit": UNIT, "ms_per_launch": ms, "walks": nw,
             "pairs": pairs, "K": Kc, "pi": "one-hot (top-1 form)", "lambda2": lam2,
-            "kernel": "sg_async_kernel<ATOMIC=true,NEG=5> (20 walker warps: SGNS per walk; 4 service warps: tcgen05 3xTF32 o3 tiles per community)",
+            "kernel": "sg_async_kernel<ATOMIC=true,NEG=5> (20 walker warps: SGNS per walk; 8 service warps: gather + tcgen05 3xTF32 o3 tiles per community)",
             "achieved": v * B_PAIR / 1e9, "peak": peak, "achieved_unit": "GB/s (7168 B x pair-updates/s)",
             "frac_of_hbm_peak": v * B_PAIR / 1e9 / peak, "o3_tflops_3xtf32": v * 3 * 2 * d * d / 1e12,
             "finite": bool(torch.isfinite(node).all())}
@@ -713,6 +713,25 @@ def run_secondary_block(wl, flush):
         out["o2_other_sizes"] = res
     except Exception as e:
         out["o2_other_sizes"] = {"error": repr(e)}
+    # o1 at sizes 64 / 256 on the same edge list (o1_hogwild_dx_kernel), with the any-size kernel beside it
+    try:
+        res = {}
+        for dsz in (64, 256):
+            nh, _ = init_tables_host(n, dsz, seed=4)
+            nd = (torch.from_numpy(nh).cuda() * 0.05).contiguous()
+            row = {}
+            for tag, variant in (("specialised", _lib.VARIANT_DEFAULT), ("generic", _lib.VARIANT_GENERIC)):
+                with _lib.opts(variant=variant):
+                    ms = _timed(lambda: K.o1_batch(nd, edges, None, cfg["lr"], neg, wl.table, mode=K.MODE_HOGWILD,
+                                                   flags=K.F_ATOMIC, base_seed=3, edge_stride=stride), 1, 2, flush)
+                row[tag] = {"value": 2 * E / (ms * 1e-3), "ms_per_launch": ms}
+            row.update({"unit": "directed-updates/s", "algorithmic_bytes_per_update": 4 * dsz * 8,
+                        "achieved_gbs": row["specialised"]["value"] * 4 * dsz * 8 / 1e9})
+            res["size_%d" % dsz] = row
+            del nd
+        out["o1_other_sizes"] = res
+    except Exception as e:
+        out["o1_other_sizes"] = {"error": repr(e)}
     # walker alone
     nw = 10 * n
     L = cfg["L"]

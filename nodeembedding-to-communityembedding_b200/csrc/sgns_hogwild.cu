@@ -520,21 +520,12 @@ struct RowV {
     float4 v[NV];
 };
 
-template <bool ATOMIC, int NEG, int NV, bool HALF>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogwild_dx_kernel(const O2Params P) {
-    static_assert(NEG >= 1 && NEG <= 7 && (NV == 1 || NV == 2) && !(HALF && NV != 1), "shape");
-    constexpr int D = HALF ? 64 : 128 * NV;
-    constexpr LcgJump<NEG> J{};
-    __shared__ float lut[EXP_TABLE_SIZE];
-    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int W = P.window;
-    const float lr = P.lr, lambda = P.lambda;
-    float *const node_l = P.node + (HALF ? 2 : 4) * lane, *const ctx_l = P.ctx + (HALF ? 2 : 4) * lane;
-    const Draw draw = P.draw;
-    // HALF: the lane's two elements travel in .x/.y, .z/.w stay +0 (fma(0, 0, acc) == acc: the sums are untouched)
-    auto LD = [&](const float *p) {
+// HALF: the lane's two elements travel in .x/.y, .z/.w stay +0 (fma(0, 0, acc) == acc: the sums are untouched)
+template <int NV, bool HALF>
+struct RowOps {
+    static constexpr int D = HALF ? 64 : 128 * NV;
+    static constexpr int LANE_STRIDE = HALF ? 2 : 4;  // elements between consecutive lanes' pointers
+    static __device__ __forceinline__ RowV<NV> ld(const float *p) {
         RowV<NV> r;
         if (HALF) {
             const float2 t = __ldcg(reinterpret_cast<const float2 *>(p));
@@ -544,24 +535,24 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogw
             for (int m = 0; m < NV; m++) r.v[m] = ldcg4(p + 128 * m);
         }
         return r;
-    };
-    auto ST = [&](float *p, const RowV<NV> &r) {
+    }
+    static __device__ __forceinline__ void st(float *p, const RowV<NV> &r) {
         if (HALF) {
             *reinterpret_cast<float2 *>(p) = make_float2(r.v[0].x, r.v[0].y);
         } else {
 #pragma unroll
             for (int m = 0; m < NV; m++) st4(p + 128 * m, r.v[m]);
         }
-    };
-    auto RED = [&](float *p, const RowV<NV> &r) {
+    }
+    static __device__ __forceinline__ void red(float *p, const RowV<NV> &r) {
         if (HALF) {
             asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(r.v[0].x), "f"(r.v[0].y) : "memory");
         } else {
 #pragma unroll
             for (int m = 0; m < NV; m++) red_add4(p + 128 * m, r.v[m]);
         }
-    };
-    auto DOT = [&](const RowV<NV> &a, const RowV<NV> &b) {  // the any-size kernel's order: element index ascending
+    }
+    static __device__ __forceinline__ float dot(const RowV<NV> &a, const RowV<NV> &b) {  // element index ascending
         float acc = 0.f;
 #pragma unroll
         for (int m = 0; m < NV; m++) {
@@ -571,27 +562,50 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogw
             acc = fmaf(a.v[m].w, b.v[m].w, acc);
         }
         return acc;
-    };
-    auto FMA = [&](RowV<NV> &y, float g, const RowV<NV> &x) {  // y += g * x
+    }
+    static __device__ __forceinline__ void fma(RowV<NV> &y, float g, const RowV<NV> &x) {  // y += g * x
 #pragma unroll
         for (int m = 0; m < NV; m++) {
             y.v[m].x = fmaf(g, x.v[m].x, y.v[m].x); y.v[m].y = fmaf(g, x.v[m].y, y.v[m].y);
             y.v[m].z = fmaf(g, x.v[m].z, y.v[m].z); y.v[m].w = fmaf(g, x.v[m].w, y.v[m].w);
         }
-    };
-    auto MUL = [&](float g, const RowV<NV> &x) {
+    }
+    static __device__ __forceinline__ RowV<NV> mul(float g, const RowV<NV> &x) {
         RowV<NV> r;
 #pragma unroll
         for (int m = 0; m < NV; m++)
             r.v[m] = make_float4(__fmul_rn(g, x.v[m].x), __fmul_rn(g, x.v[m].y), __fmul_rn(g, x.v[m].z), __fmul_rn(g, x.v[m].w));
         return r;
-    };
-    auto ZERO = [&]() {
+    }
+    static __device__ __forceinline__ RowV<NV> zero() {
         RowV<NV> r;
 #pragma unroll
         for (int m = 0; m < NV; m++) r.v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
         return r;
-    };
+    }
+    static __device__ __forceinline__ RowV<NV> add(const RowV<NV> &a, const RowV<NV> &b) {
+        RowV<NV> r;
+#pragma unroll
+        for (int m = 0; m < NV; m++)
+            r.v[m] = make_float4(a.v[m].x + b.v[m].x, a.v[m].y + b.v[m].y, a.v[m].z + b.v[m].z, a.v[m].w + b.v[m].w);
+        return r;
+    }
+};
+
+template <bool ATOMIC, int NEG, int NV, bool HALF>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogwild_dx_kernel(const O2Params P) {
+    static_assert(NEG >= 1 && NEG <= 7 && (NV == 1 || NV == 2) && !(HALF && NV != 1), "shape");
+    using R = RowOps<NV, HALF>;
+    constexpr int D = R::D;
+    constexpr LcgJump<NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int W = P.window;
+    const float lr = P.lr, lambda = P.lambda;
+    float *const node_l = P.node + (HALF ? 2 : 4) * lane, *const ctx_l = P.ctx + (HALF ? 2 : 4) * lane;
+    const Draw draw = P.draw;
     uint64_t myA = 1, myC = 0;
 #pragma unroll
     for (int k = 0; k < NEG; k++)
@@ -620,13 +634,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogw
             const uint32_t wi = __ldg(path + i);
             if (wi == COMEMB_TOKEN_NONE) continue;
             float *pos_ptr = ctx_l + (int64_t)wi * D;
-            RowV<NV> cpos = LD(pos_ptr), dpos = ZERO();
+            RowV<NV> cpos = R::ld(pos_ptr), dpos = R::zero();
             const int j1 = min(len, i + W + 1);
             for (int j = max(0, i - W); j < j1; j++) {  // pyx:503
                 const uint32_t wj = __ldg(path + j);
                 if (j == i || wj == COMEMB_TOKEN_NONE) continue;
                 float *row1_ptr = node_l + (int64_t)wj * D;
-                const RowV<NV> r1 = LD(row1_ptr);
+                const RowV<NV> r1 = R::ld(row1_ptr);
                 const uint32_t tmine = tnext;
                 tnext = (lane < NEG) ? draw_fetch(draw, (myA * rnd + myC) & LCG_MASK) : 0xFFFFFF00u + lane;
                 rnd = (J.A[NEG] * rnd + J.C[NEG]) & LCG_MASK;
@@ -638,15 +652,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogw
                 for (int k = 1; k < NEG; k++)
 #pragma unroll
                     for (int a = 0; a < k; a++) anydup = anydup || (t[a] == t[k]);
-                RowV<NV> work = ZERO();
+                RowV<NV> work = R::zero();
                 if (!anydup) {
                     RowV<NV> c[NEG];
 #pragma unroll
-                    for (int k = 0; k < NEG; k++) c[k] = LD(ctx_l + (int64_t)t[k] * D);
+                    for (int k = 0; k < NEG; k++) c[k] = R::ld(ctx_l + (int64_t)t[k] * D);
                     float p[8];
-                    p[0] = DOT(r1, cpos);
+                    p[0] = R::dot(r1, cpos);
 #pragma unroll
-                    for (int k = 0; k < 7; k++) p[k + 1] = k < NEG ? DOT(r1, c[k < NEG ? k : 0]) : 0.f;
+                    for (int k = 0; k < 7; k++) p[k + 1] = k < NEG ? R::dot(r1, c[k < NEG ? k : 0]) : 0.f;
                     const float fm = reduce8_transposed(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], lane);
                     bool live = pi == 0;
 #pragma unroll
@@ -656,33 +670,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogw
                         gm = __fmul_rn(__fmul_rn(my_label - lut[lut_index(fm)], lr), lambda);
                     {
                         const float g = __shfl_sync(FULL, gm, lane_of_p(0));
-                        FMA(work, g, cpos);  // pyx:146
-                        if (ATOMIC) FMA(dpos, g, r1);
-                        FMA(cpos, g, r1);  // pyx:147 (registers)
+                        R::fma(work, g, cpos);  // pyx:146
+                        if (ATOMIC) R::fma(dpos, g, r1);
+                        R::fma(cpos, g, r1);  // pyx:147 (registers)
                     }
 #pragma unroll
                     for (int k = 0; k < NEG; k++) {
                         const float g = __shfl_sync(FULL, gm, lane_of_p(k + 1));
-                        FMA(work, g, c[k]);  // pyx:146
+                        R::fma(work, g, c[k]);  // pyx:146
                         if (g != 0.f) {
                             float *cp = ctx_l + (int64_t)t[k] * D;
                             if (ATOMIC) {
-                                RED(cp, MUL(g, r1));
+                                R::red(cp, R::mul(g, r1));
                             } else {  // pyx:147
                                 RowV<NV> nc = c[k];
-                                FMA(nc, g, r1);
-                                ST(cp, nc);
+                                R::fma(nc, g, r1);
+                                R::st(cp, nc);
                             }
                         }
                     }
                 } else {  // equal samples inside one pair: target by target, re-reading rows
                     {
-                        const float f = warp_sum_xor(DOT(r1, cpos));
+                        const float f = warp_sum_xor(R::dot(r1, cpos));
                         if (f > -MAX_EXP_F && f < MAX_EXP_F) {
                             const float g = sgns_g(f, 1.f, lr, lambda, lut);
-                            FMA(work, g, cpos);
-                            if (ATOMIC) FMA(dpos, g, r1);
-                            FMA(cpos, g, r1);
+                            R::fma(work, g, cpos);
+                            if (ATOMIC) R::fma(dpos, g, r1);
+                            R::fma(cpos, g, r1);
                         }
                     }
 #pragma unroll 1
@@ -690,35 +704,35 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o2_hogw
                         const uint32_t tk = __shfl_sync(FULL, tmine, k);
                         if (tk == wi) continue;  // pyx:135-136
                         float *cp = ctx_l + (int64_t)tk * D;
-                        const RowV<NV> c = LD(cp);
-                        const float f = warp_sum_xor(DOT(r1, c));
+                        const RowV<NV> c = R::ld(cp);
+                        const float f = warp_sum_xor(R::dot(r1, c));
                         if (f <= -MAX_EXP_F || f >= MAX_EXP_F) continue;  // pyx:141-142
                         const float g = sgns_g(f, 0.f, lr, lambda, lut);
-                        FMA(work, g, c);
+                        R::fma(work, g, c);
                         if (ATOMIC) {
-                            RED(cp, MUL(g, r1));
+                            R::red(cp, R::mul(g, r1));
                         } else {
                             RowV<NV> nc = c;
-                            FMA(nc, g, r1);
-                            ST(cp, nc);
+                            R::fma(nc, g, r1);
+                            R::st(cp, nc);
                         }
                     }
                 }
                 if (ATOMIC) {  // pyx:149
-                    RED(row1_ptr, work);
+                    R::red(row1_ptr, work);
                 } else {
                     RowV<NV> nr;
 #pragma unroll
                     for (int m = 0; m < NV; m++)
                         nr.v[m] = make_float4(r1.v[m].x + work.v[m].x, r1.v[m].y + work.v[m].y, r1.v[m].z + work.v[m].z,
                                               r1.v[m].w + work.v[m].w);
-                    ST(row1_ptr, nr);
+                    R::st(row1_ptr, nr);
                 }
             }
             if (ATOMIC)
-                RED(pos_ptr, dpos);
+                R::red(pos_ptr, dpos);
             else
-                ST(pos_ptr, cpos);
+                R::st(pos_ptr, cpos);
         }
     }
 }
@@ -921,6 +935,85 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3) o1_hogwild_d128_kerne
     }
 }
 
+// ---- o1, sizes 64 and 256: o1_hogwild_d128_kernel with another row width (RowOps, as o2_hogwild_dx_kernel) -------------------
+template <bool ATOMIC, int NEG, int NV, bool HALF>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, NV == 1 ? 3 : 2) o1_hogwild_dx_kernel(const O1Params P) {
+    static_assert(NEG >= 1 && NEG <= 7 && (NV == 1 || NV == 2) && !(HALF && NV != 1), "shape");
+    using R = RowOps<NV, HALF>;
+    constexpr int D = R::D;
+    constexpr LcgJump<2 * NEG> J{};
+    __shared__ float lut[EXP_TABLE_SIZE];
+    for (int e = threadIdx.x; e < EXP_TABLE_SIZE; e += blockDim.x) lut[e] = P.glut[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const float lr = P.lr;
+    float *const node_l = P.node + R::LANE_STRIDE * lane;
+    uint64_t myA = 1, myC = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * NEG; k++)
+        if (lane == k) {
+            myA = J.A[k];
+            myC = J.C[k];
+        }
+    const int pi = ((lane >> 4) & 1) << 2 | ((lane >> 3) & 1) << 1 | ((lane >> 2) & 1);
+    const float my_label = pi == 0 ? 1.f : 0.f;
+    const int64_t warp0 = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+
+    // one directed update (fast_o1): row x against `target` (label 1) and samples tt[0..NEG) (label 0); returns work
+    auto directed = [&](const RowV<NV> &x, const RowV<NV> &target, uint32_t word_index, const uint32_t (&tt)[NEG],
+                        const RowV<NV> (&c)[NEG]) -> RowV<NV> {
+        float p[8];
+        p[0] = R::dot(x, target);
+#pragma unroll
+        for (int k = 0; k < 7; k++) p[k + 1] = k < NEG ? R::dot(x, c[k < NEG ? k : 0]) : 0.f;
+        const float fm = reduce8_transposed(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], lane);
+        bool live = pi == 0;
+#pragma unroll
+        for (int k = 0; k < NEG; k++) live = live || (pi == k + 1 && tt[k] != word_index);  // pyx:234-235
+        float gm = 0.f;
+        if (live && fm > -MAX_EXP_F && fm < MAX_EXP_F) gm = __fmul_rn(my_label - lut[lut_index(fm)], lr);  // pyx:243
+        RowV<NV> work = R::zero();
+        R::fma(work, __shfl_sync(FULL, gm, lane_of_p(0)), target);
+#pragma unroll
+        for (int k = 0; k < NEG; k++) R::fma(work, __shfl_sync(FULL, gm, lane_of_p(k + 1)), c[k]);  // pyx:245
+        return work;
+    };
+
+    for (int64_t u = warp0; u < P.n_edges; u += n_warps) {
+        const int64_t q = P.stride > 1 ? (int64_t)(((uint64_t)u * (uint64_t)P.stride) % (uint64_t)P.n_edges) : u;
+        const uint32_t e0 = __ldg(P.edges + 2 * q), e1 = __ldg(P.edges + 2 * q + 1);
+        const uint64_t rnd = P.seeds ? P.seeds[q] : (splitmix64(P.base_seed ^ splitmix64((uint64_t)q)) & LCG_MASK);
+        const uint32_t tmine = (lane < 2 * NEG) ? draw_fetch(P.draw, (myA * rnd + myC) & LCG_MASK) : 0u;
+        float *p0 = node_l + (int64_t)e0 * D, *p1 = node_l + (int64_t)e1 * D;
+        RowV<NV> r0 = R::ld(p0);
+        RowV<NV> r1 = (e1 == e0) ? r0 : R::ld(p1);
+        uint32_t ta[NEG], tb[NEG];
+        RowV<NV> ca[NEG], cb[NEG];
+#pragma unroll
+        for (int k = 0; k < NEG; k++) {
+            ta[k] = __shfl_sync(FULL, tmine, k);
+            tb[k] = __shfl_sync(FULL, tmine, NEG + k);
+            ca[k] = R::ld(node_l + (int64_t)ta[k] * D);
+        }
+        // pyx:444: row e0 against target e1
+        RowV<NV> work = directed(r0, r1, e1, ta, ca);
+        if (ATOMIC) R::red(p0, work);
+        r0 = R::add(r0, work);
+        if (!ATOMIC) R::st(p0, r0);
+        if (e1 == e0) r1 = r0;
+        // pyx:447: row e1 against the UPDATED row e0; samples equal to e0 must see that update too.  The second
+        // direction's sample rows are loaded here (after the first direction) to halve the registers held at once.
+#pragma unroll
+        for (int k = 0; k < NEG; k++) cb[k] = tb[k] == e0 ? r0 : R::ld(node_l + (int64_t)tb[k] * D);
+        work = directed(r1, r0, e0, tb, cb);
+        if (ATOMIC)
+            R::red(p1, work);
+        else
+            R::st(p1, R::add(r1, work));
+    }
+}
+
 template <typename K>
 int grid_for(K kernel, int64_t n_units, size_t dyn_smem = 0) {
     int dev = 0, sms = 0, per_sm = 0;
@@ -1083,6 +1176,34 @@ int launch_o1_hogwild(float *node, int size, const uint32_t *edges, int64_t n_ed
             default: break;
         }
 #undef COMEMB_O1
+    }
+    if ((size == 64 || size == 256) && negative >= 1 && negative <= 7 && comemb_opts().variant != COMEMB_VARIANT_GENERIC &&
+        (reinterpret_cast<uintptr_t>(node) & 15) == 0) {  // the specialised instruction stream at another row width
+#define COMEMB_O1X(N)                                                                 \
+    case N:                                                                           \
+        if (size == 64) {                                                             \
+            if (atomic) {                                                             \
+                auto k = o1_hogwild_dx_kernel<true, N, 1, true>;                      \
+                k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);        \
+            } else {                                                                  \
+                auto k = o1_hogwild_dx_kernel<false, N, 1, true>;                     \
+                k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);        \
+            }                                                                         \
+        } else {                                                                      \
+            if (atomic) {                                                             \
+                auto k = o1_hogwild_dx_kernel<true, N, 2, false>;                     \
+                k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);        \
+            } else {                                                                  \
+                auto k = o1_hogwild_dx_kernel<false, N, 2, false>;                    \
+                k<<<grid_for(k, P.n_edges), WARPS_PER_BLOCK * 32, 0, st>>>(P);        \
+            }                                                                         \
+        }                                                                             \
+        return (int)cudaGetLastError();
+        switch (negative) {
+            COMEMB_O1X(1) COMEMB_O1X(2) COMEMB_O1X(3) COMEMB_O1X(4) COMEMB_O1X(5) COMEMB_O1X(6) COMEMB_O1X(7)
+            default: break;
+        }
+#undef COMEMB_O1X
     }
     if (size <= 128) return vec ? launch_o1_t<1, true>(P, atomic, st) : launch_o1_t<1, false>(P, atomic, st);
     if (size <= 256) return vec ? launch_o1_t<2, true>(P, atomic, st) : launch_o1_t<2, false>(P, atomic, st);

@@ -526,6 +526,37 @@ def test_o1_hogwild_d128_specialised_and_generic_kernels(K, variant):
         _lib.check(_lib.load().comemb_set_tuning(0, 0, 0))
 
 
+@pytest.mark.parametrize("atomic", [False, True])
+@pytest.mark.parametrize("d,neg,N", [(64, 5, 100), (64, 1, 12), (64, 7, 6), (256, 5, 100), (256, 3, 8), (256, 7, 30),
+                                     (64, 4, 3), (256, 2, 3)])
+def test_o1_hogwild_sizes_64_256_specialised_kernels(K, d, neg, N, atomic):
+    """Sizes 64 / 256 with negative in 1..7 take o1_hogwild_dx_kernel (size 64: two elements per lane -> the oracle's
+    DOT_WARP2 order; size 256: two float4 per lane -> DOT_WARP); one edge per launch: bit-exact against the oracle in
+    plain-store mode, and equal to the generic kernel (variant 9) in both modes -- self loops, samples that hit the
+    edge's own endpoints (tables of 3..12 rows)."""
+    from comemb_b200 import _lib
+    c = dict(cases.O1_CASES["o1_d128"], d=d, neg=neg, N=N, E=60, seed=990 + neg + d, selfloop_every=7)
+    node, table, edges = cases.o1_inputs(c)
+    seeds = O.seeds_from_numpy(np.random.RandomState(4), len(edges))
+    flags = K.F_ATOMIC if atomic else 0
+    got = {}
+    for variant in (_lib.VARIANT_DEFAULT, _lib.VARIANT_GENERIC):
+        dn, dt = dev(node), dev(table)
+        with _lib.opts(variant=variant):
+            for e, s in zip(edges, seeds):
+                K.o1_batch(dn, dev(e.reshape(1, 2)), dev(np.array([s], np.uint64)), c["lr"], neg, dt, mode=K.MODE_HOGWILD,
+                           flags=flags)
+        got[variant] = host(dn)
+    if d == 256:  # same element -> lane layout in both kernels: same bits
+        assert np.array_equal(got[_lib.VARIANT_DEFAULT], got[_lib.VARIANT_GENERIC])
+    else:         # size 64: another summation order (two elements per lane instead of four on 16 lanes)
+        assert np.abs(got[_lib.VARIANT_DEFAULT] - got[_lib.VARIANT_GENERIC]).max() <= 1e-5
+    if not atomic:
+        want = node.copy()
+        O.o1_edges(want, edges, seeds, c["lr"], neg, table, O.DOT_WARP2 if d == 64 else O.DOT_WARP)
+        assert np.array_equal(got[_lib.VARIANT_DEFAULT], want)
+
+
 def test_o1_hogwild_single_warp_equals_oracle_warp_order(K):
     for name in ("o1_d128", "o1_d2", "o1_d100_selfloops", "o1_neg0"):
         c = cases.O1_CASES[name]
