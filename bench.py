@@ -311,7 +311,14 @@ class O2Workload(object):
                                              self.stream.cuda_stream))
         off = torch.arange(n_eval + 1, dtype=torch.int64, device="cuda") * self.L
         tot, cnt = K.o2_pos_loss(self.node, self.ctx, w.reshape(-1), off, cfg["W"])
-        return {"o2_pos_loss_per_pair": tot / max(cnt, 1), "pairs": cnt, "untrained": float(np.log(2.0))}
+        # the objective the kernel descends (positive + `neg` sampled negative terms, exact sigmoids) on a tenth of those
+        # walks; the positive term alone rises above ln 2 in the first passes (5 negatives per positive pull every dot
+        # product down before the community structure separates), the objective falls from (1 + neg) ln 2
+        from comemb_b200.evaluation import sgns_objective
+        obj, pos, n_obj = sgns_objective(self.node, self.ctx, w[:max(1, n_eval // 10)], cfg["W"], self.table, cfg["neg"])
+        return {"o2_pos_loss_per_pair": tot / max(cnt, 1), "pairs": cnt, "untrained": float(np.log(2.0)),
+                "sgns_objective_per_pair": obj, "sgns_objective_untrained": float((1 + cfg["neg"]) * np.log(2.0)),
+                "sgns_objective_pairs": n_obj}
 
 
 def timed_o2_leg(wl, steps, warmup, flush):

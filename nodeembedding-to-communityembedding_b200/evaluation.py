@@ -105,3 +105,41 @@ def o2_positive_loss(model, walks, walk_off, window):
     from .utils import training_sdg_inner as K
     s, n = K.o2_pos_loss(model.node_embedding, model.context_embedding, walks, walk_off, window)
     return s / max(1, n)
+
+
+def sgns_objective(node, ctx, walks2d, window, table, negative, seed=0, max_centres=200000):
+    """The skip-gram negative-sampling objective the o2 path minimises, per (centre, context) pair, with exact sigmoids:
+        -log sigma(x_j . c_i) - sum_{t in `negative` draws from `table`} log sigma(-x_j . c_t)
+    evaluated in torch on the device the tables live on, over the window pairs of `walks2d` ([n_walks, L] row tokens,
+    TOKEN_NONE padded).  Untrained tables (context table zero) give (1 + negative) * ln 2 (less the skipped draws).  Returns (objective per pair,
+    positive part per pair, number of pairs).  An evaluator, not part of the SGD path."""
+    import torch
+    none = 0xFFFFFFFF
+    w = walks2d.long() & 0xFFFFFFFF
+    n_walks, L = w.shape
+    gen = torch.Generator(device=w.device)
+    gen.manual_seed(int(seed))
+    tot = pos_tot = 0.0
+    cnt = 0
+    tab = table.long() & 0xFFFFFFFF
+    rows_per_chunk = max(1, int(max_centres // L))
+    for r0 in range(0, n_walks, rows_per_chunk):
+        wc = w[r0:r0 + rows_per_chunk]
+        for off in range(1, int(window) + 1):
+            for a, b in ((wc[:, off:], wc[:, :-off]), (wc[:, :-off], wc[:, off:])):  # (centre i, context j) both ways
+                ok = (a != none) & (b != none)
+                ci, xj = a[ok], b[ok]
+                if ci.numel() == 0:
+                    continue
+                x = node[xj].double()
+                f = (x * ctx[ci].double()).sum(1)
+                p = torch.nn.functional.softplus(-f)
+                loss = p.clone()
+                t = tab[torch.randint(tab.numel(), (ci.numel(), int(negative)), generator=gen, device=w.device)]
+                fn = (x[:, None, :] * ctx[t].double()).sum(2)
+                live = t != ci[:, None]  # pyx:135-136: a draw equal to the centre is skipped
+                loss += (torch.nn.functional.softplus(fn) * live).sum(1)
+                tot += float(loss.sum())
+                pos_tot += float(p.sum())
+                cnt += int(ci.numel())
+    return tot / max(cnt, 1), pos_tot / max(cnt, 1), cnt

@@ -376,3 +376,36 @@ def test_micro_f1_device_method_matches_sklearn():
     b = node_classification_micro_f1(torch.from_numpy(x), y, seed=1, method="device")
     assert 0.5 < a < 0.999
     assert abs(a - b) <= 0.01, (a, b)
+
+
+def test_sgns_objective_evaluator_cpu():
+    """evaluation.sgns_objective: (1 + neg) ln 2 (minus the skipped draws) for a zero context table; the positive part equals a direct numpy
+    evaluation over the window pairs (None tokens skipped); the pair count matches pyx:494-507's loop."""
+    import torch
+    from comemb_b200.evaluation import sgns_objective
+    rs = np.random.RandomState(5)
+    n, d, L, W, neg = 50, 16, 12, 3, 4
+    node = torch.from_numpy(rs.normal(size=(n, d)).astype(np.float32) * 0.3)
+    ctx = torch.from_numpy(rs.normal(size=(n, d)).astype(np.float32) * 0.3)
+    walks = rs.randint(0, n, size=(9, L)).astype(np.int64)
+    walks[2, 5:] = 0xFFFFFFFF
+    walks[4, 3] = 0xFFFFFFFF
+    table = torch.from_numpy(rs.randint(0, n, size=1000).astype(np.int32))
+    w32 = torch.from_numpy(walks.astype(np.uint32).view(np.int32))
+    obj0, pos0, cnt = sgns_objective(node, torch.zeros_like(ctx), w32, W, table, neg)
+    # draws equal to the centre are skipped (2 % of them on a 50-row table): slightly below (1 + neg) ln 2
+    assert (1 + 0.9 * neg) * np.log(2) < obj0 <= (1 + neg) * np.log(2) + 1e-9 and abs(pos0 - np.log(2)) < 1e-9
+    want, pairs = 0.0, 0
+    for path in walks:
+        for i in range(L):
+            if path[i] == 0xFFFFFFFF:
+                continue
+            for j in range(max(0, i - W), min(L, i + W + 1)):
+                if j == i or path[j] == 0xFFFFFFFF:
+                    continue
+                f = float(node[path[j]].double() @ ctx[path[i]].double())
+                want += np.log1p(np.exp(-f))
+                pairs += 1
+    obj, pos, cnt = sgns_objective(node, ctx, w32, W, table, neg)
+    assert cnt == pairs and abs(pos - want / pairs) < 1e-9
+    assert obj > pos
