@@ -204,7 +204,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 PARTITION = "replicated"
@@ -585,7 +585,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": "failed: %r" % (e,)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -900,7 +900,7 @@ def run_secondary(args):
                     "dense_pi_form_value": n / (ms_dense * 1e-3), "flop_per_node": 2 * d * d,
                     "roofline": {"bound": "fp64-fma", "achieved_gflops": v * 2 * d * d / 1e9,
                                  "hbm_bytes_per_node": 2 * d * 4, "hbm_gbs": v * 2 * d * 4 / 1e9}})
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -933,6 +933,30 @@ def main():
     args = ap.parse_args()
     global PARTITION
     PARTITION = args.partition
+    # stdout carries exactly one line -- the JSON; anything libraries print on the way (NCCL's version / INFO lines go to
+    # stdout) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _dispatch(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        if _JSON_LINES:
+            sys.stdout.write("\n".join(_JSON_LINES) + "\n")
+            sys.stdout.flush()
+
+
+_JSON_LINES = []
+
+
+def emit(line):
+    _JSON_LINES.append(json.dumps(line))
+
+
+def _dispatch(args):
     if args.workload == "youtube":
         CFG.clear()
         CFG.update(CFG_YOUTUBE)
