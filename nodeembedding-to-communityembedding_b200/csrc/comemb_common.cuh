@@ -150,6 +150,9 @@ __device__ __forceinline__ void st4_hint(float *p, float4 v, uint64_t pol) {
                  "f"(v.w), "l"(pol)
                  : "memory");
 }
+__device__ __forceinline__ void st_f32_hint(float *p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t pol) {
     uint32_t v;
     asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));

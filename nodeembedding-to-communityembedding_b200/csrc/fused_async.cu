@@ -34,7 +34,13 @@
 #include "fused_sgns.cuh"
 #include "umma.cuh"
 
+#ifndef COMEMB_ASYNC_STATS
+#define COMEMB_ASYNC_STATS 0  // 1: per-phase cycle counters (printed with COMEMB_ROUND_STATS=1); they cost the 48-register
+#endif                        //    service warps local-memory spills, so the product build leaves them out
+
 namespace {
+constexpr bool STATS = COMEMB_ASYNC_STATS != 0;
+__device__ __forceinline__ long long tick() { return STATS ? clock64() : 0LL; }
 
 using fused::INFO_INWARP;
 constexpr int D = 128;
@@ -45,7 +51,7 @@ constexpr int NSVC = 4;                     // warps per service team (one per T
 constexpr int ASYNC_WARPS = 28;             // warps per CTA: 8 service + 20 walkers.  896 threads leave 72 registers per thread at
                                             // launch; the service warpgroups give registers back (setmaxnreg.dec -> 48) and the
                                             // walker warpgroups take them (setmaxnreg.inc -> 80), like the 24-warp build
-constexpr int SVC_REGS = 48, WALK_REGS = 80;
+constexpr int SVC_REGS = 48, WALK_REGS = 80;  // (56 / 80 would use the whole register file exactly: setmaxnreg.inc then never returns)
 constexpr int MAXQ = 64;                    // ints of front-team scratch
 constexpr int WCTX = 2;                     // walks interleaved per walker warp
 constexpr unsigned long long EMPTY = ~0ULL;
@@ -78,6 +84,7 @@ struct AsyncParams {
     unsigned long long *walk_cursor;
     int *err;
     long long *stats;
+    int y_hint;                 // 1: L2 evict_first on the result-slot stores and loads
     int64_t cap;                // ring capacity (power of two >= all requests that can be outstanding)
     int n_rep, Q, vslots;
     int64_t active_warps;
@@ -224,11 +231,13 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         int cur_c = -1, empty_scans = 0;
         bool a_pending = false;
         long long tiles = 0, rows_served = 0, idle_polls = 0;
-        long long ph[6] = {0, 0, 0, 0, 0, 0}, tp = clock64();
+        long long ph[6] = {0, 0, 0, 0, 0, 0}, tp = tick();
         auto lap = [&](int k) {
-            const long long now = clock64();
-            ph[k] += now - tp;
-            tp = now;
+            if (STATS) {
+                const long long now = clock64();
+                ph[k] += now - tp;
+                tp = now;
+            }
         };
         // Pick the next tile: every front thread looks at the queues t, t+128, ...; the queue with the largest backlog wins,
         // the resident community gets a bonus of 1.5 tiles (a switch costs a 128 KB operand fetch), and the thread that saw
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             choose_and_claim();  // the next tile is claimed while the tensor cores work on this one
             lap(4);
         }
-        if (P.stats && tid == 0) {
+        if (STATS && P.stats && tid == 0) {
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 0), (unsigned long long)tiles);
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 1), (unsigned long long)rows_served);
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 2), (unsigned long long)idle_polls);
@@ -394,19 +403,21 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         const uint32_t a_hi = umma::smem_u32(smem + L::A_HI), a_lo = umma::smem_u32(smem + L::A_LO);
         const uint32_t b_hi = umma::smem_u32(smem + L::B_HI), b_lo = umma::smem_u32(smem + L::B_LO);
         uint32_t par_a = 0;
-        long long t_wait = 0, t_epi = 0, tq = clock64(), bph[4] = {0, 0, 0, 0};
+        long long t_wait = 0, t_epi = 0, tq = tick(), bph[4] = {0, 0, 0, 0};
         auto blap = [&](int k) {
-            const long long now = clock64();
-            bph[k] += now - tq;
-            t_epi += now - tq;
-            tq = now;
+            if (STATS) {
+                const long long now = clock64();
+                bph[k] += now - tq;
+                t_epi += now - tq;
+                tq = now;
+            }
         };
         for (uint32_t u = 0;; u++) {
             const uint32_t b = u & 1u;
             umma::mbar_wait(bar_ent + b, (u >> 1) & 1u);  // the front team has popped the tile's entries (rows, slots, mu_c)
             const int n = n_s[b];
             if (n < 0) break;
-            { const long long now = clock64(); t_wait += now - tq; tq = now; }
+            if (STATS) { const long long now = clock64(); t_wait += now - tq; tq = now; }
             const int n16 = (n + 15) & ~15;
             // the other half of the B operand (rows 4+w, 12+w, ...); the previous tile's MMAs were waited for below
             gather_rows<4>(P, smem + L::B_HI, smem + L::B_LO, row_s + b * TN, reinterpret_cast<const float *>(smem + L::MU), NSVC + bw,
@@ -432,13 +443,18 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             blap(1);
             const uint32_t *slot_b = slot_s + b * TN;
             const int a = 32 * bw + lane;
+            const uint64_t y_pol = l2_policy_evict_first();
             for (int ch = 0; ch * 16 < n16; ch++) {
                 float v[16];
                 umma::tmem_ld16(taddr + ((uint32_t)(32 * bw) << 16) + b * (uint32_t)TN + (uint32_t)(ch * 16), v);
 #pragma unroll
                 for (int qq = 0; qq < 16; qq++) {
                     const int nn = ch * 16 + qq;
-                    if (nn < n) P.ybuf[(int64_t)slot_b[nn] * D + a] = v[qq];  // Y itself: the requester applies its responsibility
+                    if (nn < n) {  // Y itself: the requester applies its responsibility
+                        float *yp = P.ybuf + (int64_t)slot_b[nn] * D + a;
+                        if (P.y_hint) st_f32_hint(yp, v[qq], y_pol);
+                        else *yp = v[qq];
+                    }
                 }
             }
             umma::tc_fence_before();
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             if (lane == 0) mbar_arrive(bar_free + b);  // 4 arrivals: list and accumulator b are free for tile u+2
             blap(3);
         }
-        if (P.stats && btid == 0) {
+        if (STATS && P.stats && btid == 0) {
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 14), (unsigned long long)t_wait);
             atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 15), (unsigned long long)t_epi);
             for (int k = 0; k < 4; k++) atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 16 + k), (unsigned long long)bph[k]);
@@ -470,7 +486,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
         const bool walker = gwarp * WCTX < P.active_warps;  // active_warps counts walk CONTEXTS (the Hogwild concurrency cap)
         fused::SgnsArgs SA;
         SA.node = P.node; SA.ctx = P.ctx; SA.table = P.table; SA.mod = P.mod; SA.mu = P.mu; SA.inv_cov = P.inv_cov;
-        SA.weight = P.weight; SA.pi = nullptr; SA.ybuf = P.ybuf; SA.K = K; SA.dense = false; SA.o3_on = true;
+        SA.weight = P.weight; SA.pi = nullptr; SA.ybuf = P.ybuf; SA.K = K; SA.dense = false; SA.o3_on = true; SA.y_evict_first = P.y_hint != 0;
         SA.is_node = P.is_node != 0; SA.lr = P.lr; SA.lambda1 = P.lambda1; SA.nl2 = -P.lambda2;            // c:3132
         SA.clipv = __double2float_rn(__dmul_rn((double)P.lr, 0.1));                                         // c:2556
         uint64_t myA = 1, myC = 0;
@@ -581,12 +597,12 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
 
         int remaining = 0;
         {
-            const long long t0 = clock64();
+            const long long t0 = tick();
             for (int c = 0; c < WCTX; c++) {
                 stage(c);
                 remaining += cx[c].have;
             }
-            t_stage += clock64() - t0;
+            t_stage += tick() - t0;
         }
         for (int c = 0; remaining > 0; c = (c + 1) % WCTX) {
             if (!cx[c].have) continue;
@@ -612,7 +628,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             ok = __shfl_sync(FULL, ok, 0);
             __syncwarp();
             if (!ok) break;
-            const long long t2 = clock64();
+            const long long t2 = tick();
             // ---- [sgns] -----------------------------------------------------------------------------------------------------
             {
                 const uint64_t r0 = cx[c].rnd;
@@ -625,20 +641,22 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 if (lane == 0) cx[c].rnd = lcg_skip(r0, (uint64_t)V * (uint64_t)NEG);  // V pairs consumed NEG draws each
                 __syncwarp();
             }
-            const long long t3 = clock64();
+            const long long t3 = tick();
             stage(c);
             if (!cx[c].have) remaining--;
-            const long long t4 = clock64();
-            t_wait += t2 - t1;
-            t_sgns += t3 - t2;
-            t_stage += t4 - t3;
-            centres++;
+            if (STATS) {
+                const long long t4 = clock64();
+                t_wait += t2 - t1;
+                t_sgns += t3 - t2;
+                t_stage += t4 - t3;
+                centres++;
+            }
         }
         __syncwarp();
         if (walker && lane == 0) {
             __threadfence();
             atomicSub(P.live, 1);
-            if (P.stats && centres) {
+            if (STATS && P.stats && centres) {
                 atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 3), (unsigned long long)t_stage);
                 atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 4), (unsigned long long)t_wait);
                 atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 5), (unsigned long long)t_sgns);
@@ -733,8 +751,9 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     P.tail = reinterpret_cast<unsigned *>(scratch + o_ctl + 256);
     P.claim = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 32);
     P.done = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 64);
+    P.y_hint = 1;  // +2 % on the SBM workload: the 60 MB of result slots stop displacing table rows (L2 hit rate 67 %)
     P.cap = cap; P.n_rep = n_rep; P.Q = Q; P.vslots = vslots; P.active_warps = warps;
-    static const bool want_stats = getenv("COMEMB_ROUND_STATS") != nullptr;
+    static const bool want_stats = STATS && getenv("COMEMB_ROUND_STATS") != nullptr;  // needs -DCOMEMB_ASYNC_STATS=1
     long long *d_stats = nullptr;
     if (want_stats) {
         cudaMalloc(&d_stats, 24 * sizeof(long long));

@@ -28,6 +28,7 @@ struct SgnsArgs {
     int K;
     bool dense, o3_on, is_node;
     float lr, lambda1, nl2, clipv;
+    bool y_evict_first = false;  // result slots are written once and read once: keep them from displacing table rows in L2
 };
 
 __device__ __forceinline__ float clipf(float v, float c) { return fminf(fmaxf(v, -c), c); }
@@ -61,7 +62,7 @@ __device__ __forceinline__ void sgns_centre(const SgnsArgs &P, const uint32_t wi
             const int inf = infS[v];
             if (!(inf & INFO_INWARP) && (dense || inf >= 0)) {  // taken from the tensor-core result
                 float *yp = P.ybuf + (slot0 + v) * D + 4 * lane;
-                y = __ldcg(reinterpret_cast<const float4 *>(yp));
+                y = P.y_evict_first ? ldcg4_hint(yp, l2_policy_evict_first()) : __ldcg(reinterpret_cast<const float4 *>(yp));
                 if (dense)
                     __stcg(reinterpret_cast<float4 *>(yp), make_float4(0.f, 0.f, 0.f, 0.f));
                 else
