@@ -441,14 +441,17 @@ def run_ours(args):
         nh, ch = runner.host_tables()  # the caller's host tables live in page-locked memory
         nh[...] = wl.node.cpu().numpy()
         ch[...] = wl.ctx.cpu().numpy()
+        pw, po, ps = runner.host_walk_buffers(wh.size, offh.size - 1)  # ... and so do its walks, offsets and seeds
+        pw[...], po[...], ps[...] = wh, offh, seeds_h
+        wh, offh, seeds_h = pw, po, ps
         for s in range(1 + max(1, args.steps // 2)):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             h2d, d2h = runner.run(nh, ch, wh, offh, seeds_h, lr, neg, W, mode=K.MODE_HOGWILD, flags=flags)
             if s:
                 ms.append(time.perf_counter() - t0)
-        how = ("HostO2Runner.run: host numpy tables (page-locked) + walks + seeds -> HBM, Hogwild o2 kernel, both tables "
-               "back to host, every step")
+        how = ("HostO2Runner.run: host numpy tables, walks and seeds (all page-locked) -> HBM, Hogwild o2 kernel, both "
+               "tables back to host, every step")
         del runner
     else:
         # row-partitioned tables: this rank's walks and seeds come from page-locked host memory every step, the kernel

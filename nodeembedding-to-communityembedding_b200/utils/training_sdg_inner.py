@@ -240,6 +240,13 @@ class HostO2Runner(object):
         pageable->pinned staging copy (pass these same arrays to run())."""
         return self.h_node.numpy(), self.h_ctx.numpy()
 
+    def host_walk_buffers(self, n_tokens, n_walks):
+        """numpy views (walks uint32 [n_tokens], walk_off int64 [n_walks+1], seeds uint64 [n_walks]) of the runner's
+        page-locked input buffers: a producer that writes its walks here and passes these views to run() avoids the
+        pageable->pinned staging copy, like host_tables() for the tables."""
+        return (self.h_walks.numpy()[:n_tokens].view(np.uint32), self.h_off.numpy()[:n_walks + 1],
+                self.h_seeds.numpy()[:n_walks].view(np.uint64))
+
     def run(self, node, ctx, walks, walk_off, seeds, lr, negative, window, alpha=1.0, mode=MODE_HOGWILD, flags=0):
         """node/ctx: numpy float32 [N,d] updated in place; walks uint32 flat; walk_off int64; seeds uint64.
         Returns (h2d_bytes, d2h_bytes)."""
@@ -250,9 +257,12 @@ class HostO2Runner(object):
         if not own:
             self.h_node.numpy()[...] = node
             self.h_ctx.numpy()[...] = ctx
-        self.h_walks.numpy()[:nt] = walks.view(np.int32)
-        self.h_off.numpy()[:nw + 1] = walk_off
-        self.h_seeds.numpy()[:nw] = seeds.view(np.int64)
+        if walks.ctypes.data != self.h_walks.data_ptr():
+            self.h_walks.numpy()[:nt] = walks.view(np.int32)
+        if walk_off.ctypes.data != self.h_off.data_ptr():
+            self.h_off.numpy()[:nw + 1] = walk_off
+        if seeds.ctypes.data != self.h_seeds.data_ptr():
+            self.h_seeds.numpy()[:nw] = seeds.view(np.int64)
         self.d_node.copy_(self.h_node, non_blocking=True)
         self.d_ctx.copy_(self.h_ctx, non_blocking=True)
         self.d_walks[:nt].copy_(self.h_walks[:nt], non_blocking=True)

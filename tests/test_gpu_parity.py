@@ -1010,6 +1010,12 @@ def test_host_o2_runner_equals_device_resident_call(K):
     pc[...] = ctx
     runner.run(pn, pc, flat, off, seeds, c["lr"], c["neg"], c["W"], mode=K.MODE_ORDERED)
     assert np.array_equal(pn, host(dn)) and np.array_equal(pc, host(dc))
+    pw, po, ps = runner.host_walk_buffers(flat.size, len(walks))  # ... and caller-owned page-locked walks / offsets / seeds
+    pw[...], po[...], ps[...] = flat, off, seeds
+    pn[...] = node
+    pc[...] = ctx
+    runner.run(pn, pc, pw, po, ps, c["lr"], c["neg"], c["W"], mode=K.MODE_ORDERED)
+    assert np.array_equal(pn, host(dn)) and np.array_equal(pc, host(dc))
 
 
 def test_replica_trainer_single_process_and_model_persistence(K, tmp_path):
