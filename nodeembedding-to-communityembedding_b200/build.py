@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(CSRC, src[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("COMEMB_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

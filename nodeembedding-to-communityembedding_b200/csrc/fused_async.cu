@@ -45,7 +45,13 @@ __device__ __forceinline__ long long tick() { return STATS ? clock64() : 0LL; }
 using fused::INFO_INWARP;
 constexpr int D = 128;
 constexpr int TN = 64;                      // requests per GEMM tile (tcgen05 N)
-constexpr int VMAX = 64;                    // window rows per centre (2*window <= 64)
+#ifndef COMEMB_VMAX
+#define COMEMB_VMAX 64
+#endif
+#ifndef COMEMB_WCTX
+#define COMEMB_WCTX 2
+#endif
+constexpr int VMAX = COMEMB_VMAX;           // window rows per centre (2*window <= VMAX)
 constexpr int A_IMG_BYTES = 2 * D * D * 4;  // hi + lo operand images of one community
 constexpr int NSVC = 4;                     // warps per service team (one per TMEM lane quarter): front = warps 0..3, back = 4..7
 constexpr int ASYNC_WARPS = 28;             // warps per CTA: 8 service + 20 walkers.  896 threads leave 72 registers per thread at
@@ -53,7 +59,7 @@ constexpr int ASYNC_WARPS = 28;             // warps per CTA: 8 service + 20 wal
                                             // walker warpgroups take them (setmaxnreg.inc -> 80), like the 24-warp build
 constexpr int SVC_REGS = 48, WALK_REGS = 80;  // (56 / 80 would use the whole register file exactly: setmaxnreg.inc then never returns)
 constexpr int MAXQ = 64;                    // ints of front-team scratch
-constexpr int WCTX = 2;                     // walks interleaved per walker warp
+constexpr int WCTX = COMEMB_WCTX;           // walks interleaved per walker warp
 constexpr unsigned long long EMPTY = ~0ULL;
 constexpr long long WAIT_TIMEOUT = 8000000000LL;  // ~4 s of SM clocks: a protocol bug must end the kernel, not hang the GPU
 
