@@ -57,7 +57,11 @@ constexpr int NSVC = 4;                     // warps per service team (one per T
 constexpr int ASYNC_WARPS = 28;             // warps per CTA: 8 service + 20 walkers.  896 threads leave 72 registers per thread at
                                             // launch; the service warpgroups give registers back (setmaxnreg.dec -> 48) and the
                                             // walker warpgroups take them (setmaxnreg.inc -> 80), like the 24-warp build
-constexpr int SVC_REGS = 48, WALK_REGS = 80;  // (56 / 80 would use the whole register file exactly: setmaxnreg.inc then never returns)
+constexpr int SVC_REGS = 48, WALK_REGS = 80;
+// Registers are allocated per SM sub-partition (16384 each; warp w lives on sub-partition w % 4): with the 8 service warps
+// first, a sub-partition holds 2 service warps and ceil((ASYNC_WARPS - 8) / 4) walkers.  A split that does not fit there --
+// or fits exactly (56 / 80 at 28 warps, 48 / 88 at 26) -- leaves setmaxnreg.inc waiting forever.
+static_assert((2 * SVC_REGS + ((ASYNC_WARPS - 8 + 3) / 4) * WALK_REGS) * 32 <= 16384 - 512, "register split per sub-partition");
 constexpr int MAXQ = 64;                    // ints of front-team scratch
 constexpr int WCTX = COMEMB_WCTX;           // walks interleaved per walker warp
 constexpr unsigned long long EMPTY = ~0ULL;
