@@ -409,3 +409,22 @@ def test_sgns_objective_evaluator_cpu():
     obj, pos, cnt = sgns_objective(node, ctx, w32, W, table, neg)
     assert cnt == pairs and abs(pos - want / pairs) < 1e-9
     assert obj > pos
+
+
+def test_c_abi_argument_errors_return_status_codes_without_a_gpu():
+    """The argument checks of the C ABI run before any CUDA call: null pointers / negative sizes give COMEMB_E_ARG (-1),
+    shapes no kernel covers COMEMB_E_UNSUPPORTED (-2), a launch before comemb_init() COMEMB_E_NOINIT (-3), each with a
+    message -- the error behaviour the host mirror turns into exceptions (ComembError)."""
+    from comemb_b200 import _lib
+    lib = _lib.load()
+    assert lib.comemb_gmm_mstep(None, 10, 128, None, None, 3, None, None) == -1
+    assert lib.comemb_gmm_mstep(1, 10, 64, 1, 1, 3, 1, None) == -2
+    assert lib.comemb_gmm_estep(None, 10, 128, None, None, 3, None, None) == -1
+    assert lib.comemb_gmm_estep(1, 10, 64, 1, 1, 3, 1, None) == -2
+    assert lib.comemb_set_max_warps(-1) == -1 and lib.comemb_set_tuning(-1, 0, 0) == -1
+    st = lib.comemb_o2_walks(None, None, 10, 128, None, None, 1, None, 0, None, 0, None, 0, 5, 5, 0.1, 1.0, 0, 0, None, None)
+    assert st in (-1, -3)
+    for code, word in ((-1, b"invalid argument"), (-2, b"unsupported"), (-3, b"comemb_init")):
+        assert word in lib.comemb_error_string(code)
+    with pytest.raises(_lib.ComembError):
+        _lib.check(-2)
