@@ -17,6 +17,8 @@
 // to oracle/comemb_oracle.c and to the reference's golden vectors (tests/test_gpu_parity.py::test_o2_flow_*).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "comemb_common.cuh"
@@ -302,7 +304,8 @@ int launch_o2_flow(float *node, float *ctx, int64_t n_rows, const uint32_t *walk
     }
 
     // chunks of whole walks with at most `cap` touches (a single longer walk forms its own chunk)
-    const int64_t cap = 1LL << 27;
+    int64_t cap = 1LL << 27;
+    if (const char *e = getenv("COMEMB_FLOW_CHUNK_TOUCHES")) cap = std::max<int64_t>(1, atoll(e));  // tests: force several chunks
     int64_t biggest = 0;
     for (int64_t a = 0; a < n_walks;) {
         int64_t b = a + 1;

@@ -133,6 +133,23 @@ def test_o2_flow_kernel_vs_oracle(K, N, nw, L, neg, W, none_every, max_warps):
     assert n == int((flat != 0xFFFFFFFF).sum())
 
 
+def test_o2_flow_kernel_chunked_corpus(K, monkeypatch):
+    """The dataflow replay processes a corpus in chunks of whole walks (scratch for at most 2^27 touches at a time);
+    with the chunk size forced down to ~3 walks per chunk (COMEMB_FLOW_CHUNK_TOUCHES) the result is still the oracle's,
+    bit for bit -- a chunk boundary is a kernel boundary, every ticket counter restarts."""
+    from comemb_b200 import _lib
+    monkeypatch.setenv("COMEMB_FLOW_CHUNK_TOUCHES", "6000")
+    c = dict(cases.O2_CASES["o2_d128_small"], N=500, neg=5, nw=40, L=30, W=5, seed=9400, ragged=True, none_every=11)
+    node, ctx, table, walks = cases.o2_inputs(c)
+    flat, off = cases.flatten_walks(walks)
+    seeds = O.seeds_from_numpy(np.random.RandomState(16), len(walks))
+    dn, dc = dev(node), dev(ctx)
+    with _lib.opts(variant=_lib.VARIANT_ORDERED_FLOW):
+        K.o2_batch(dn, dc, dev(flat), dev(off), dev(seeds), c["lr"], 5, 5, dev(table), mode=K.MODE_ORDERED)
+    O.o2_walks(node, ctx, flat, off, seeds, c["lr"], 5, 5, table, 1.0, O.DOT_REFBLAS_QUIRK)
+    assert np.array_equal(host(dn), node) and np.array_equal(host(dc), ctx)
+
+
 def test_o2_flow_kernel_equals_one_cta_replay_at_scale(K):
     """50 000 rows, 3 000 walks of 40 (1 M pair updates): the dataflow replay and the one-CTA kernel produce the same
     bits; hashed per-walk seeds (no seed array)."""
