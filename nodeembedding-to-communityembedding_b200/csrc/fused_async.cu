@@ -95,6 +95,7 @@ struct AsyncParams {
     int *err;
     long long *stats;
     int y_hint;                 // 1: L2 evict_first on the result-slot stores and loads
+    int stick;                  // a CTA leaves its resident community only for a queue with more than `stick` times its backlog
     int64_t cap;                // ring capacity (power of two >= all requests that can be outstanding)
     int n_rep, Q, vslots;
     int64_t active_warps;
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
         };
         // Pick the next tile: every front thread looks at the queues t, t+128, ...; the queue with the largest backlog wins,
-        // the resident community gets a bonus of 1.5 tiles (a switch costs a 128 KB operand fetch), and the thread that saw
+        // the resident community counts `stick` (2) times plus 1.5 tiles (a switch costs a 128 KB operand fetch from L2:
+        // with plain largest-backlog-first 31 % of the tiles switched, +10 % L2 traffic; measured +5 %), and the thread that saw
         // the winner claims up to TN of its entries with one compare-and-swap (any CTA may serve any community: the load
         // balances itself).  Result in pick[]; count 0 = nothing claimed, -1 = all walkers finished and all queues empty.
         auto choose_and_claim = [&]() {
@@ -262,7 +264,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
                 const int backlog = (int)(ld_vol(P.tail + q * 8) - h);
                 if (backlog > 0) {
                     // + a CTA-specific tie-breaker so that the CTAs do not all rush to the same queue
-                    const int score = min(backlog, 1 << 19) + (q == cur_c ? (3 * TN) / 2 : 0) + ((q * 7 + (int)blockIdx.x * 13) & 31);
+                    const int score = min(backlog, 1 << 16) * (q == cur_c ? P.stick : 1) + (q == cur_c ? (3 * TN) / 2 : 0) +
+                                      ((q * 7 + (int)blockIdx.x * 13) & 31);
                     const int k2 = (score << 11) | q;
                     if (k2 > key) {
                         key = k2;
@@ -368,6 +371,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             if (t >= 1) umma::mbar_wait(bar_mma + ((t - 1u) & 1u), ((t - 1u) >> 1) & 1u);
             a_pending = false;
             if (c != cur_c) {
+                if (STATS) idle_polls += 1LL << 32;  // high half: community switches
                 if (tid == 0) {
                     umma::mbar_expect_tx(bar_a, A_IMG_BYTES);
                     const char *src = P.a_img + (int64_t)c * A_IMG_BYTES;
@@ -761,7 +765,9 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
     P.tail = reinterpret_cast<unsigned *>(scratch + o_ctl + 256);
     P.claim = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 32);
     P.done = reinterpret_cast<unsigned *>(scratch + o_ctl + 256 + (size_t)Q * 64);
-    P.y_hint = 1;  // +2 % on the SBM workload: the 60 MB of result slots stop displacing table rows (L2 hit rate 67 %)
+    static const int stick_env = getenv("COMEMB_FUSED_STICK") ? atoi(getenv("COMEMB_FUSED_STICK")) : 2;
+    P.stick = stick_env < 1 ? 1 : (stick_env > 16 ? 16 : stick_env);
+    P.y_hint = 1;  // +4.5 % on the SBM workload: the 60 MB of result slots stop displacing table rows in L2
     P.cap = cap; P.n_rep = n_rep; P.Q = Q; P.vslots = vslots; P.active_warps = warps;
     static const bool want_stats = STATS && getenv("COMEMB_ROUND_STATS") != nullptr;  // needs -DCOMEMB_ASYNC_STATS=1
     long long *d_stats = nullptr;
@@ -787,9 +793,9 @@ int launch_sg_fused_async(float *node, float *negemb, const uint32_t *walks, con
         cudaMemcpy(&h_err, P.err, 4, cudaMemcpyDeviceToHost);
         cudaFree(d_stats);
         fprintf(stderr,
-                "[async stats] grid %d n_rep %d Q %d err %d: tiles %lld rows %lld (%.1f rows/tile) idle polls %lld | per centre "
+                "[async stats] grid %d n_rep %d Q %d err %d: tiles %lld rows %lld (%.1f rows/tile) idle polls %lld community switches %lld | per centre "
                 "cycles: stage %lld wait %lld sgns %lld (centres %lld)\n",
-                grid, n_rep, Q, h_err, h[0], h[1], h[0] ? (double)h[1] / h[0] : 0.0, h[2], h[3] / (h[6] + 1),
+                grid, n_rep, Q, h_err, h[0], h[1], h[0] ? (double)h[1] / h[0] : 0.0, h[2] & 0xFFFFFFFFLL, h[2] >> 32, h[3] / (h[6] + 1),
                 h[4] / (h[6] + 1), h[5] / (h[6] + 1), h[6]);
         fprintf(stderr, "[async stats] front cycles per tile: wait-free %lld pop %lld gather %lld issue %lld claim-next %lld | back: "
                 "wait %lld epilogue+signal %lld\n",
