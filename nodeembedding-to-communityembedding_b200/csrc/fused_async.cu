@@ -158,24 +158,26 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Rows r = first, first + 8, first + 16, ... (< n) of the tile: gather from the node table, subtract mu_c, split hi/lo TF32 and
-// store into the swizzled B operand images.  Each service team takes every other group of four rows (front: first = warp,
-// back: first = 4 + warp), GB rows in flight per warp.
-template <int GB>
+// Rows r = first, first + STRIDE, ... (COUNT of them, those < n) of the tile: gather from the node table, subtract mu_c,
+// split hi/lo TF32 and store into the swizzled B operand images, GB rows in flight per warp.  The tile's 64 rows are dealt
+// out in 16 classes r mod 16: front warp w takes classes w, w + 4, w + 8 (12 rows), back warp w class 12 + w (4 rows) --
+// the back team also drains the accumulators and signals, the front team would otherwise wait for it.
+template <int GB, int STRIDE, int COUNT>
 __device__ __forceinline__ void gather_rows(const AsyncParams &P, char *b_hi_img, char *b_lo_img, const uint32_t *row_b,
                                             const float *mu_s, int first, int n, int lane) {
+    static_assert(COUNT % GB == 0, "batches");
     const float4 m = *reinterpret_cast<const float4 *>(mu_s + 4 * lane);
 #pragma unroll
-    for (int half = 0; half < 8 / GB; half++) {
+    for (int i0 = 0; i0 < COUNT; i0 += GB) {
         float4 xv[GB];
 #pragma unroll
         for (int qq = 0; qq < GB; qq++) {
-            const int r = first + 8 * (half * GB + qq);
+            const int r = first + STRIDE * (i0 + qq);
             if (r < n) xv[qq] = __ldcg(reinterpret_cast<const float4 *>(P.node + (int64_t)row_b[r] * D + 4 * lane));
         }
 #pragma unroll
         for (int qq = 0; qq < GB; qq++) {
-            const int r = first + 8 * (half * GB + qq);
+            const int r = first + STRIDE * (i0 + qq);
             if (r < n) {
                 const float4 x = xv[qq];
                 const float4 df = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
@@ -388,7 +390,9 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             lap(1);
             if (tid == 0) mbar_arrive(bar_ent + b);  // the back team may start on its half of the rows
             // ---- B operand, this team's half (rows w, w+8, ...): gathers in flight 4 at a time -----------------------------
-            gather_rows<4>(P, smem + L::B_HI, smem + L::B_LO, row_b, mu_s, warp, n, lane);
+#pragma unroll
+            for (int cls = 0; cls < 3; cls++)
+                gather_rows<4, 16, TN / 16>(P, smem + L::B_HI, smem + L::B_LO, row_b, mu_s, warp + 4 * cls, n, lane);
             umma::fence_proxy_async_smem();
             front_barrier();
             lap(2);
@@ -433,9 +437,9 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             if (n < 0) break;
             if (STATS) { const long long now = clock64(); t_wait += now - tq; tq = now; }
             const int n16 = (n + 15) & ~15;
-            // the other half of the B operand (rows 4+w, 12+w, ...); the previous tile's MMAs were waited for below
-            gather_rows<4>(P, smem + L::B_HI, smem + L::B_LO, row_s + b * TN, reinterpret_cast<const float *>(smem + L::MU), NSVC + bw,
-                           n, lane);
+            // the last quarter of the B operand (rows 12+w, 28+w, ...); the previous tile's MMAs were waited for below
+            gather_rows<4, 16, TN / 16>(P, smem + L::B_HI, smem + L::B_LO, row_s + b * TN,
+                                        reinterpret_cast<const float *>(smem + L::MU), 3 * NSVC + bw, n, lane);
             umma::fence_proxy_async_smem();
             back_barrier();
             blap(0);
