@@ -160,8 +160,7 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
 
 // Rows r = first, first + STRIDE, ... (COUNT of them, those < n) of the tile: gather from the node table, subtract mu_c,
 // split hi/lo TF32 and store into the swizzled B operand images, GB rows in flight per warp.  The tile's 64 rows are dealt
-// out in 16 classes r mod 16: front warp w takes classes w, w + 4, w + 8 (12 rows), back warp w class 12 + w (4 rows) --
-// the back team also drains the accumulators and signals, the front team would otherwise wait for it.
+// out in 16 classes r mod 16; front warp w takes classes w, w + 4, w + 8, w + 12.
 template <int GB, int STRIDE, int COUNT>
 __device__ __forceinline__ void gather_rows(const AsyncParams &P, char *b_hi_img, char *b_lo_img, const uint32_t *row_b,
                                             const float *mu_s, int first, int n, int lane) {
@@ -388,15 +387,17 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             }
             front_barrier();
             lap(1);
-            if (tid == 0) mbar_arrive(bar_ent + b);  // the back team may start on its half of the rows
-            // ---- B operand, this team's half (rows w, w+8, ...): gathers in flight 4 at a time -----------------------------
+            if (tid == 0) mbar_arrive(bar_ent + b);  // the tile's slots and size are published to the back team
+            // ---- B operand: warp w gathers rows w, w+4, ... (16 each), 4 in flight.  The back team's loop (MMAs -> drain the
+            // accumulator -> result stores -> signals) is the longer one, so the whole gather stays here: splitting it between
+            // the teams was measured at 7.15e8 (half / half), 7.5e8 (three quarters here) and 7.8e8 (all here) -----------------
 #pragma unroll
-            for (int cls = 0; cls < 3; cls++)
+            for (int cls = 0; cls < 4; cls++)
                 gather_rows<4, 16, TN / 16>(P, smem + L::B_HI, smem + L::B_LO, row_b, mu_s, warp + 4 * cls, n, lane);
             umma::fence_proxy_async_smem();
             front_barrier();
             lap(2);
-            if (tid == 0) mbar_arrive(bar_full + b);  // this half of the B operand is in place; the back team issues the MMAs
+            if (tid == 0) mbar_arrive(bar_full + b);  // the B operand is in place; the back team issues the MMAs
                                                       // (issuing blocks the thread for about their duration: off this path)
             a_pending = false;
             t++;
@@ -437,13 +438,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sg_async_kernel(const AsyncParams 
             if (n < 0) break;
             if (STATS) { const long long now = clock64(); t_wait += now - tq; tq = now; }
             const int n16 = (n + 15) & ~15;
-            // the last quarter of the B operand (rows 12+w, 28+w, ...); the previous tile's MMAs were waited for below
-            gather_rows<4, 16, TN / 16>(P, smem + L::B_HI, smem + L::B_LO, row_s + b * TN,
-                                        reinterpret_cast<const float *>(smem + L::MU), 3 * NSVC + bw, n, lane);
-            umma::fence_proxy_async_smem();
-            back_barrier();
             blap(0);
-            umma::mbar_wait(bar_full + b, (u >> 1) & 1u);  // ... and the front team's half
+            umma::mbar_wait(bar_full + b, (u >> 1) & 1u);  // the front team has written the B operand
             if (bw == 0) {
                 if (n_s[2 + b]) {  // this tile switched the community: its operand images are still in flight
                     umma::mbar_wait(bar_a, par_a);
