@@ -4,10 +4,11 @@
 //
 // The o3 term is a 128x128 mat-vec per pair against the inverse covariance of x_j's community; a window holds ~4.5
 // communities, so a warp alone can batch only ~4 rows per community (round 1 streamed 64 KB of inv_cov from L2 per such
-// group).  Here the batching is done ACROSS the ~3000 walks in flight, asynchronously:
+// group).  Here the batching is done ACROSS the ~5900 walks in flight, asynchronously:
 //
-//   one CTA per SM; 16 WALKER warps + 8 SERVICE warps (a front and a back team of 4) per CTA.
-//   walker warp (owns a walk, one centre at a time, exactly the o2 kernel's order):
+//   one CTA per SM; 20 WALKER warps + 8 SERVICE warps (a front and a back team of 4) per CTA; setmaxnreg gives the walkers
+//   80 registers and the service warps 48.
+//   walker warp (interleaves two walks; per walk one centre at a time, exactly the o2 kernel's order):
 //     [stage]  lists the rows of its next window; every row whose o3 term can be taken from the row's value at the start
 //              of the centre (all but a node that repeats inside the window) becomes a request {row, result slot} appended
 //              to the queue of (its community, replica) -- a ring in global memory, tail reserved with one warp-aggregated
@@ -16,14 +17,14 @@
 //     [sgns]   the centre's pairs (fused_sgns.cuh): SGNS on the o2 size-128 code path + the combined write with the o3
 //              term from its result slots; repeated nodes get the term in-warp from the current value, so a walk sees the
 //              reference's sequential semantics exactly.
-//   service, front team: looks at all queues, takes the fullest (the resident community is favoured), claims up to 64
+//   service, front team: looks at all queues, takes the fullest (the resident community counts twice), claims up to 64
 //   entries with one CAS (any CTA serves any community: the load balances itself), keeps inv_cov_c resident in shared
 //   memory as the tcgen05 A operand (hi/lo TF32 images, fetched by the TMA engine with cp.async.bulk only on a community
-//   switch), gathers the rows, forms x - mu_c, splits hi/lo into the swizzled B operand, and one thread issues 48
-//   tcgen05.mma (3xTF32: fp32-level accuracy) into one of two TMEM accumulators;
-//   service, back team: waits for the tile's MMAs, reads the accumulator back with tcgen05.ld, writes Y to the result
-//   slots, release-increments the requesters' counters and hands the buffer back -- while the front team is already
-//   two steps into the next tile.
+//   switch), gathers the rows, forms x - mu_c and splits hi/lo into the swizzled B operand;
+//   service, back team: one thread issues 48 tcgen05.mma (3xTF32: fp32-level accuracy) into one of two TMEM accumulators,
+//   the team waits for them, reads the accumulator back with tcgen05.ld, writes Y to the result slots (L2 evict_first),
+//   release-increments the requesters' counters and hands the buffer back -- while the front team is already claiming
+//   and gathering the next tile.
 //
 // Nothing waits on a barrier that another CTA must reach: walkers wait only for results, service warps only for
 // published entries, so the SGNS half runs at the o2 kernel's pace while the tensor half hides behind it.
